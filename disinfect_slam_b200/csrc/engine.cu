@@ -1,0 +1,612 @@
+// engine.cu -- host side of libtsdf_b200.so: buffer ownership, streams, launch sequencing and the
+// C ABI declared in include/tsdf_b200.h.  Replaces the host part of TSDFGrid
+// (utils/tsdf/voxel_tsdf.cu:309-506): no per-frame host synchronisation inside Integrate except
+// the final one the synchronous API requires, no cudaMalloc/cudaFree per gather, double-buffered
+// frame staging so that the upload of frame k+1 overlaps the kernels of frame k.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../include/tsdf_b200.h"
+#include "tsdf_device.cuh"
+#include "tsdf_launch.h"
+
+using namespace tsdf;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                            \
+  do {                                                                                                      \
+    cudaError_t e_ = (call);                                                                                \
+    if (e_ != cudaSuccess) return fail(TSDF_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                                 \
+  } while (0)
+
+namespace {
+enum { PH_UPLOAD = 0, PH_ALLOC, PH_SELECT, PH_INTEGRATE, PH_RAYCAST, PH_GATHER, PH_COUNT };
+
+struct FrameBuf {
+  unsigned char* rgb = nullptr; float *depth = nullptr, *ht = nullptr, *lt = nullptr;
+  TexA* texA = nullptr; TexB* texB = nullptr;
+  cudaEvent_t uploaded = nullptr, done = nullptr;
+  int* h_ctr = nullptr;  // pinned copy of the device counters after this frame
+  bool in_flight = false;
+};
+}  // namespace
+
+struct tsdf_engine {
+  int device = 0, num_sms = 148;
+  float voxel_size = 0, truncation = 0;
+  tsdf_config cfg{};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  DeviceState S{};
+  FrameBuf fb[2];
+  int cur = 0;
+  int last_slot = -1;  // slot of the most recent frame (its counters are the "last" ones)
+  int* visible = nullptr; int* selected = nullptr;
+  uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
+  float4* gather_out = nullptr; size_t gather_cap = 0; int64_t gather_n = 0;
+  int* h_scalar = nullptr;  // pinned scratch (16 ints)
+  int n_active = 0;         // host mirror after the last completed frame
+  tsdf_counters last{};
+  bool profiling = false;
+  // phase profiling: (begin, end) event pairs recorded on the launching stream, summed lazily
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs[PH_COUNT];
+  cudaEvent_t ev_open[PH_COUNT] = {};
+  double phase_total_ms[PH_COUNT] = {};
+  int64_t phase_count[PH_COUNT] = {};
+  tsdf_counters totals{};  // sums over the frames retired since tsdf_set_profiling(1)
+  int64_t total_frames = 0;
+};
+
+// ---- small host helpers (same float32 arithmetic as the reference's host code) -------------------
+static Intr intr_inverse(const Intr& k) {  // utils/cuda/camera.cuh:35-39
+  const float fxi = 1 / k.fx, fyi = 1 / k.fy;
+  Intr r; r.fx = fxi; r.fy = fyi; r.cx = -k.cx * fxi; r.cy = -k.cy * fyi; return r;
+}
+static Pose pose_inverse(const Pose& T) {  // utils/cuda/lie_group.cuh:25-27 + Eigen quaternion inverse
+  Pose r;
+  const float n2 = (T.qx * T.qx + T.qy * T.qy) + (T.qz * T.qz + T.qw * T.qw);
+  if (n2 > 0.f) { r.qx = (-T.qx) / n2; r.qy = (-T.qy) / n2; r.qz = (-T.qz) / n2; r.qw = T.qw / n2; }
+  else { r.qx = r.qy = r.qz = r.qw = 0.f; }
+  r.tx = r.ty = r.tz = 0.f;
+  const float3 t = qrot(r, f3(-T.tx, -T.ty, -T.tz));
+  r.tx = t.x; r.ty = t.y; r.tz = t.z;
+  return r;
+}
+static FrameParams make_params(const tsdf_engine* e, int w, int h, float max_depth, const float K[4], const float q[4],
+                               const float t[3]) {
+  FrameParams P;
+  P.cam_T_world = Pose{q[0], q[1], q[2], q[3], t[0], t[1], t[2]};
+  P.world_T_cam = pose_inverse(P.cam_T_world);
+  P.K = Intr{K[0], K[1], K[2], K[3]};
+  P.Kinv = intr_inverse(P.K);
+  P.w = w; P.h = h; P.max_depth = max_depth; P.voxel_size = e->voxel_size; P.truncation = e->truncation;
+  return P;
+}
+static cudaEvent_t ev_get(tsdf_engine* e) {
+  if (!e->ev_pool.empty()) { cudaEvent_t v = e->ev_pool.back(); e->ev_pool.pop_back(); return v; }
+  cudaEvent_t v = nullptr; cudaEventCreate(&v); return v;
+}
+static void phase_begin(tsdf_engine* e, int ph, cudaStream_t st) {
+  if (!e->profiling) return;
+  e->ev_open[ph] = ev_get(e);
+  cudaEventRecord(e->ev_open[ph], st);
+}
+static void phase_end(tsdf_engine* e, int ph, cudaStream_t st) {
+  if (!e->profiling || !e->ev_open[ph]) return;
+  cudaEvent_t b = ev_get(e);
+  cudaEventRecord(b, st);
+  e->ev_pairs[ph].emplace_back(e->ev_open[ph], b);
+  e->ev_open[ph] = nullptr;
+}
+// fold all completed event pairs into the per-phase totals (call after the streams are idle)
+static void phase_collect(tsdf_engine* e) {
+  for (int ph = 0; ph < PH_COUNT; ++ph) {
+    for (auto& pr : e->ev_pairs[ph]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { e->phase_total_ms[ph] += ms; e->phase_count[ph]++; }
+      else cudaGetLastError();
+      e->ev_pool.push_back(pr.first); e->ev_pool.push_back(pr.second);
+    }
+    e->ev_pairs[ph].clear();
+  }
+}
+
+static int check_frame_args(tsdf_engine* e, const void* a, const void* b, const void* c, const void* d, int w, int h,
+                            const float* K, const float* q, const float* t) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if (!a || !b || !c || !d || !K || !q || !t) return fail(TSDF_E_INVALID, "null image / camera pointer");
+  if (w <= 0 || h <= 0 || (int64_t)w * h > e->cfg.max_image_pixels)
+    return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
+  return TSDF_OK;
+}
+
+// kernels of one frame, enqueued on the compute stream; no host synchronisation
+static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned char* rgb, const float* depth,
+                          const float* ht, const float* lt, FrameBuf& f) {
+  cudaMemsetAsync(e->S.ctr + C_NVIS, 0, sizeof(int) * (C_COUNT - C_NVIS), e->stream);
+  phase_begin(e, PH_ALLOC, e->stream);
+  launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.texA, f.texB, e->stream);
+  phase_end(e, PH_ALLOC, e->stream);
+  phase_begin(e, PH_SELECT, e->stream);
+  launch_select_visible(e->S, P, e->visible, e->num_sms, e->stream);
+  phase_end(e, PH_SELECT, e->stream);
+  phase_begin(e, PH_INTEGRATE, e->stream);
+  launch_integrate_carve(e->S, P, e->visible, f.texA, f.texB, e->num_sms, e->stream);
+  phase_end(e, PH_INTEGRATE, e->stream);
+  cudaMemcpyAsync(f.h_ctr, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream);
+  cudaEventRecord(f.done, e->stream);
+  f.in_flight = true;
+}
+
+// wait for the frame that used slot `s`, fold its counters into the host mirror, surface errors
+static int retire_slot(tsdf_engine* e, int s) {
+  FrameBuf& f = e->fb[s];
+  if (!f.in_flight) return TSDF_OK;
+  CU(cudaEventSynchronize(f.done));
+  f.in_flight = false;
+  const int* c = f.h_ctr;
+  tsdf_counters k{};
+  k.n_active_pre = e->n_active;  // frames retire in submission order
+  k.n_new = c[C_NNEW]; k.n_visible = c[C_NVIS]; k.n_carved = c[C_NCARVED]; k.n_candidates = c[C_NCAND];
+  k.n_updated = (int64_t)(((u64)(unsigned)c[C_NUPD_HI] << 32) | (unsigned)c[C_NUPD_LO]);
+  k.n_active_post = e->cfg.pool_blocks - c[C_FREE];
+  e->last = k;
+  e->n_active = (int)k.n_active_post;
+  if (e->profiling) {
+    e->totals.n_new += k.n_new; e->totals.n_visible += k.n_visible; e->totals.n_updated += k.n_updated;
+    e->totals.n_carved += k.n_carved; e->totals.n_candidates += k.n_candidates;
+    e->totals.n_active_post += k.n_active_post; e->totals.n_active_pre += k.n_active_pre;
+    e->total_frames++;
+  }
+  if (c[C_ERROR] & ERR_POOL) return fail(TSDF_E_POOL_EXHAUSTED, "voxel block pool exhausted (pool_blocks=%d)", e->cfg.pool_blocks);
+  if (c[C_ERROR] & ERR_TABLE) return fail(TSDF_E_TABLE_FULL, "hash table full (table_slots=%d)", e->cfg.table_slots);
+  // tombstone garbage collection once live + tombstoned slots exceed half of the table
+  if ((unsigned)c[C_NONEMPTY] > (e->S.table_mask + 1) / 2) launch_rehash(e->S, e->num_sms, e->stream);
+  return TSDF_OK;
+}
+static int drain(tsdf_engine* e) {
+  int rc = TSDF_OK;
+  // retire in submission order so that `last` ends up describing the newest frame
+  const int first = e->last_slot < 0 ? 0 : 1 - e->last_slot;
+  for (int i = 0; i < 2; ++i) { const int r = retire_slot(e, (first + i) & 1); if (r != TSDF_OK) rc = r; }
+  CU(cudaStreamSynchronize(e->stream));
+  return rc;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)); }
+};
+
+extern "C" {
+
+const char* tsdf_last_error(void) { return g_err; }
+int tsdf_abi_version(void) { return TSDF_B200_ABI_VERSION; }
+
+int tsdf_default_config(tsdf_config* cfg) {
+  if (!cfg) return fail(TSDF_E_INVALID, "null config");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = (int32_t)sizeof(tsdf_config);
+  cfg->device = -1;
+  cfg->pool_blocks = 1 << 18;
+  cfg->table_slots = 1 << 21;
+  cfg->max_image_pixels = 1920 * 1080;
+  cfg->shard_rank = 0; cfg->shard_count = 1; cfg->flags = 0;
+  return TSDF_OK;
+}
+
+int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg, tsdf_handle* out) {
+  if (!out) return fail(TSDF_E_INVALID, "null output handle");
+  *out = nullptr;
+  if (!(voxel_size > 0.f) || !(truncation > 0.f)) return fail(TSDF_E_INVALID, "voxel_size and truncation must be > 0");
+  tsdf_config cfg; tsdf_default_config(&cfg);
+  if (user_cfg) {
+    if (user_cfg->struct_size != (int32_t)sizeof(tsdf_config)) return fail(TSDF_E_INVALID, "tsdf_config.struct_size mismatch");
+    cfg = *user_cfg;
+  }
+  if (cfg.pool_blocks <= 0 || cfg.table_slots <= 0 || (cfg.table_slots & (cfg.table_slots - 1)))
+    return fail(TSDF_E_INVALID, "pool_blocks must be > 0 and table_slots a power of two");
+  if (cfg.table_slots < 2 * (int64_t)cfg.pool_blocks) return fail(TSDF_E_INVALID, "table_slots must be >= 2 * pool_blocks");
+  if (cfg.shard_count < 1 || cfg.shard_rank < 0 || cfg.shard_rank >= cfg.shard_count)
+    return fail(TSDF_E_INVALID, "bad shard_rank / shard_count");
+  if (cfg.max_image_pixels <= 0) return fail(TSDF_E_INVALID, "max_image_pixels must be > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TSDF_E_NO_DEVICE, "no CUDA device available (this engine has no CPU fallback)");
+  }
+  if (cfg.device < 0) CU(cudaGetDevice(&cfg.device));
+  if (cfg.device >= ndev) return fail(TSDF_E_INVALID, "device %d out of range (%d devices)", cfg.device, ndev);
+  CU(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, cfg.device));
+  if (prop.major != 10) return fail(TSDF_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg.device, prop.major, prop.minor);
+
+  tsdf_engine* e = new tsdf_engine();
+  e->device = cfg.device; e->num_sms = prop.multiProcessorCount; e->voxel_size = voxel_size; e->truncation = truncation; e->cfg = cfg;
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(TSDF_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); tsdf_destroy(e); return rc_; } } while (0)
+  CUX(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUX(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  DeviceState& S = e->S;
+  S.table_mask = (unsigned)cfg.table_slots - 1; S.pool_blocks = cfg.pool_blocks;
+  S.shard_rank = cfg.shard_rank; S.shard_count = cfg.shard_count;
+  CUX(cudaMalloc(&S.table, sizeof(Slot) * (size_t)cfg.table_slots));
+  CUX(cudaMalloc(&S.block_key, sizeof(u64) * (size_t)cfg.pool_blocks));
+  CUX(cudaMalloc(&S.voxels, (size_t)kBlockBytes * (size_t)cfg.pool_blocks));
+  CUX(cudaMalloc(&S.free_stack, sizeof(int) * (size_t)cfg.pool_blocks));
+  CUX(cudaMalloc(&S.ctr, sizeof(int) * C_COUNT));
+  CUX(cudaMalloc(&e->visible, sizeof(int) * (size_t)cfg.pool_blocks));
+  CUX(cudaMalloc(&e->selected, sizeof(int) * (size_t)cfg.pool_blocks));
+  const size_t npx = (size_t)cfg.max_image_pixels;
+  for (int i = 0; i < 2; ++i) {
+    FrameBuf& f = e->fb[i];
+    CUX(cudaMalloc(&f.rgb, 3 * npx)); CUX(cudaMalloc(&f.depth, 4 * npx)); CUX(cudaMalloc(&f.ht, 4 * npx)); CUX(cudaMalloc(&f.lt, 4 * npx));
+    CUX(cudaMalloc(&f.texA, sizeof(TexA) * npx)); CUX(cudaMalloc(&f.texB, sizeof(TexB) * npx));
+    CUX(cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
+    CUX(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    CUX(cudaMallocHost(&f.h_ctr, sizeof(int) * C_COUNT));
+    memset(f.h_ctr, 0, sizeof(int) * C_COUNT);
+  }
+  CUX(cudaMalloc(&e->rgba, sizeof(uchar4) * npx)); CUX(cudaMalloc(&e->normal, sizeof(uchar4) * npx)); CUX(cudaMalloc(&e->hit_depth, sizeof(float) * npx));
+  CUX(cudaMallocHost(&e->h_scalar, sizeof(int) * 16));
+  launch_init_state(S, e->stream);
+  CUX(cudaGetLastError());
+  CUX(cudaStreamSynchronize(e->stream));
+#undef CUX
+  *out = e;
+  return TSDF_OK;
+}
+
+int tsdf_destroy(tsdf_handle e) {
+  if (!e) return TSDF_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
+  cudaFree(e->visible); cudaFree(e->selected);
+  for (int i = 0; i < 2; ++i) {
+    FrameBuf& f = e->fb[i];
+    cudaFree(f.rgb); cudaFree(f.depth); cudaFree(f.ht); cudaFree(f.lt); cudaFree(f.texA); cudaFree(f.texB);
+    if (f.uploaded) cudaEventDestroy(f.uploaded);
+    if (f.done) cudaEventDestroy(f.done);
+    if (f.h_ctr) cudaFreeHost(f.h_ctr);
+  }
+  cudaFree(e->rgba); cudaFree(e->normal); cudaFree(e->hit_depth); cudaFree(e->gather_out);
+  if (e->h_scalar) cudaFreeHost(e->h_scalar);
+  phase_collect(e);
+  for (cudaEvent_t v : e->ev_pool) cudaEventDestroy(v);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  delete e;
+  return TSDF_OK;
+}
+
+int tsdf_integrate_async(tsdf_handle e, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int w,
+                         int h, float max_depth, const float K[4], const float q[4], const float t[3]) {
+  int rc = check_frame_args(e, rgb, depth, ht, lt, w, h, K, q, t);
+  if (rc) return rc;
+  CU(cudaSetDevice(e->device));
+  const int s = e->cur;
+  FrameBuf& f = e->fb[s];
+  rc = retire_slot(e, s);  // the frame two calls ago: bounds the pipeline depth, frees the staging set
+  if (rc) return rc;
+  const size_t n = (size_t)w * h;
+  // uploads on the copy stream (they overlap the previous frame's kernels on the compute stream)
+  phase_begin(e, PH_UPLOAD, e->copy_stream);
+  CU(cudaMemcpyAsync(f.rgb, rgb, 3 * n, cudaMemcpyHostToDevice, e->copy_stream));
+  CU(cudaMemcpyAsync(f.depth, depth, 4 * n, cudaMemcpyHostToDevice, e->copy_stream));
+  CU(cudaMemcpyAsync(f.ht, ht, 4 * n, cudaMemcpyHostToDevice, e->copy_stream));
+  CU(cudaMemcpyAsync(f.lt, lt, 4 * n, cudaMemcpyHostToDevice, e->copy_stream));
+  phase_end(e, PH_UPLOAD, e->copy_stream);
+  CU(cudaEventRecord(f.uploaded, e->copy_stream));
+  CU(cudaStreamWaitEvent(e->stream, f.uploaded, 0));
+  const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
+  enqueue_frame(e, P, f.rgb, f.depth, f.ht, f.lt, f);
+  CU(cudaGetLastError());
+  e->last_slot = s;
+  e->cur = 1 - s;
+  // the host buffers are reusable once the copies have been issued from them
+  CU(cudaEventSynchronize(f.uploaded));
+  return TSDF_OK;
+}
+
+int tsdf_integrate(tsdf_handle e, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int w, int h,
+                   float max_depth, const float K[4], const float q[4], const float t[3]) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  int rc = tsdf_integrate_async(e, rgb, depth, ht, lt, w, h, max_depth, K, q, t);
+  if (rc) return rc;
+  return drain(e);
+}
+
+int tsdf_integrate_device(tsdf_handle e, const void* d_rgb, const void* d_depth, const void* d_ht, const void* d_lt, int w,
+                          int h, float max_depth, const float K[4], const float q[4], const float t[3], void* after_event) {
+  int rc = check_frame_args(e, d_rgb, d_depth, d_ht, d_lt, w, h, K, q, t);
+  if (rc) return rc;
+  CU(cudaSetDevice(e->device));
+  const int s = e->cur;
+  FrameBuf& f = e->fb[s];
+  rc = retire_slot(e, s);
+  if (rc) return rc;
+  if (after_event) CU(cudaStreamWaitEvent(e->stream, (cudaEvent_t)after_event, 0));
+  const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
+  enqueue_frame(e, P, (const unsigned char*)d_rgb, (const float*)d_depth, (const float*)d_ht, (const float*)d_lt, f);
+  CU(cudaGetLastError());
+  e->last_slot = s;
+  e->cur = 1 - s;
+  return TSDF_OK;
+}
+
+int tsdf_synchronize(tsdf_handle e) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  return drain(e);
+}
+
+void* tsdf_stream(tsdf_handle e) { return e ? (void*)e->stream : nullptr; }
+
+int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                        void* d_rgba, void* d_normal, void* d_hit_depth, void* d_packed) {
+  if (!e || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
+  if (w <= 0 || h <= 0) return fail(TSDF_E_INVALID, "bad image size %dx%d", w, h);
+  CU(cudaSetDevice(e->device));
+  const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
+  phase_begin(e, PH_RAYCAST, e->stream);
+  launch_raycast(e->S, P, e->truncation / 2, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
+                 (unsigned long long*)d_packed, e->stream);  // step = truncation / 2, voxel_tsdf.cu:497
+  phase_end(e, PH_RAYCAST, e->stream);
+  CU(cudaGetLastError());
+  return TSDF_OK;
+}
+
+int tsdf_raycast(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                 uint8_t* rgba, uint8_t* normal, float* hit_depth) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if ((int64_t)w * h > e->cfg.max_image_pixels) return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
+  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, e->rgba, e->normal, e->hit_depth, nullptr);
+  if (rc) return rc;
+  const size_t n = (size_t)w * h;
+  if (rgba) CU(cudaMemcpyAsync(rgba, e->rgba, 4 * n, cudaMemcpyDeviceToHost, e->stream));
+  if (normal) CU(cudaMemcpyAsync(normal, e->normal, 4 * n, cudaMemcpyDeviceToHost, e->stream));
+  if (hit_depth) CU(cudaMemcpyAsync(hit_depth, e->hit_depth, 4 * n, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return TSDF_OK;
+}
+
+static int select_blocks(tsdf_engine* e, const float* bbox, int* n_sel) {
+  GridBound g{};
+  if (bbox) {  // BoundingCube::Scale<short>(1. / voxel_size), voxel_tsdf.cuh:21-26, voxel_tsdf.cu:429
+    const float scale = (float)(1. / (double)e->voxel_size);
+    auto cv = [&](float v) { float p = v * scale; if (p != p) return (short)0; p = std::max(-32768.f, std::min(32767.f, p)); return (short)(int)p; };
+    g.xmin = cv(bbox[0]); g.xmax = cv(bbox[1]); g.ymin = cv(bbox[2]); g.ymax = cv(bbox[3]); g.zmin = cv(bbox[4]); g.zmax = cv(bbox[5]);
+  }
+  CU(cudaMemsetAsync(e->S.ctr + C_NSEL, 0, sizeof(int), e->stream));
+  launch_select_blocks(e->S, bbox != nullptr, g, e->selected, e->num_sms, e->stream);
+  CU(cudaMemcpyAsync(e->h_scalar, e->S.ctr + C_NSEL, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *n_sel = e->h_scalar[0];
+  return TSDF_OK;
+}
+
+static int gather_impl(tsdf_engine* e, const float* bbox, float* out, int64_t cap, int64_t* n_voxels) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  if (rc) return rc;
+  phase_begin(e, PH_GATHER, e->stream);
+  int n_sel = 0;
+  rc = select_blocks(e, bbox, &n_sel);
+  if (rc) return rc;
+  const size_t need = (size_t)n_sel * kBlockVolume;
+  if (need > e->gather_cap) {  // grow-only result buffer instead of cudaMalloc/cudaFree per call (voxel_tsdf.cu:439-451)
+    cudaFree(e->gather_out); e->gather_out = nullptr; e->gather_cap = 0;
+    const size_t want = std::max(need, (size_t)1 << 20);
+    CU(cudaMalloc(&e->gather_out, sizeof(float4) * want));
+    e->gather_cap = want;
+  }
+  launch_download_voxels(e->S, e->selected, n_sel, e->voxel_size, e->gather_out, e->stream);
+  phase_end(e, PH_GATHER, e->stream);
+  CU(cudaGetLastError());
+  e->gather_n = (int64_t)need;
+  if (n_voxels) *n_voxels = e->gather_n;
+  if (out && cap > 0) {
+    const size_t m = (size_t)std::min<int64_t>(cap, e->gather_n);
+    if (m) CU(cudaMemcpyAsync(out, e->gather_out, sizeof(float4) * m, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return TSDF_OK;
+}
+int tsdf_gather_valid(tsdf_handle e, float* out, int64_t cap, int64_t* n) { return gather_impl(e, nullptr, out, cap, n); }
+int tsdf_gather_in_bound(tsdf_handle e, const float bbox[6], float* out, int64_t cap, int64_t* n) {
+  if (!bbox) return fail(TSDF_E_INVALID, "null bbox");
+  return gather_impl(e, bbox, out, cap, n);
+}
+int tsdf_gather_fetch(tsdf_handle e, float* out, int64_t cap) {
+  if (!e || !out) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaSetDevice(e->device));
+  const size_t m = (size_t)std::min<int64_t>(cap, e->gather_n);
+  if (m) CU(cudaMemcpyAsync(out, e->gather_out, sizeof(float4) * m, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return TSDF_OK;
+}
+int tsdf_gather_device_result(tsdf_handle e, const void** d_out, int64_t* n) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if (d_out) *d_out = e->gather_out;
+  if (n) *n = e->gather_n;
+  return TSDF_OK;
+}
+
+int tsdf_num_active_blocks(tsdf_handle e, int* n) {
+  if (!e || !n) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(e->h_scalar, e->S.ctr + C_FREE, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->n_active = e->cfg.pool_blocks - e->h_scalar[0];
+  *n = e->n_active;
+  return TSDF_OK;
+}
+
+int tsdf_get_counters(tsdf_handle e, tsdf_counters* out) {
+  if (!e || !out) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  *out = e->last;
+  return rc;
+}
+
+uint32_t tsdf_hash(int16_t bx, int16_t by, int16_t bz) { return hash_block(bx, by, bz) & ((1u << 21) - 1); }
+
+// ---- unit-test / parity access -------------------------------------------------------------------
+static int after_mutation(tsdf_engine* e) {
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(e->h_scalar, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->n_active = e->cfg.pool_blocks - e->h_scalar[C_FREE];
+  if (e->h_scalar[C_ERROR] & ERR_POOL) return fail(TSDF_E_POOL_EXHAUSTED, "voxel block pool exhausted (pool_blocks=%d)", e->cfg.pool_blocks);
+  if (e->h_scalar[C_ERROR] & ERR_TABLE) return fail(TSDF_E_TABLE_FULL, "hash table full");
+  return TSDF_OK;
+}
+
+int tsdf_allocate_blocks(tsdf_handle e, const int16_t* keys, int n) {
+  if (!e || (!keys && n > 0) || n < 0) return fail(TSDF_E_INVALID, "bad argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e); if (rc) return rc;
+  DevBuf<short> d; CU(d.alloc(3 * (size_t)n));
+  if (n) CU(cudaMemcpyAsync(d.p, keys, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
+  launch_allocate_list(e->S, d.p, n, e->stream);
+  return after_mutation(e);
+}
+int tsdf_delete_blocks(tsdf_handle e, const int16_t* keys, int n) {
+  if (!e || (!keys && n > 0) || n < 0) return fail(TSDF_E_INVALID, "bad argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e); if (rc) return rc;
+  DevBuf<short> d; CU(d.alloc(3 * (size_t)n));
+  if (n) CU(cudaMemcpyAsync(d.p, keys, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
+  launch_delete_list(e->S, d.p, n, e->stream);
+  return after_mutation(e);
+}
+int tsdf_retrieve_voxels(tsdf_handle e, const int16_t* pts, int n, float* tsdf_out, uint8_t* rgbw, float* prob, int32_t* found) {
+  if (!e || !pts || n < 0) return fail(TSDF_E_INVALID, "bad argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e); if (rc) return rc;
+  DevBuf<short> dp; DevBuf<float> dt, dpr; DevBuf<unsigned> dc; DevBuf<int> df;
+  CU(dp.alloc(3 * (size_t)n)); CU(dt.alloc(n)); CU(dpr.alloc(n)); CU(dc.alloc(n)); CU(df.alloc(n));
+  if (n) CU(cudaMemcpyAsync(dp.p, pts, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
+  launch_retrieve_list(e->S, dp.p, n, dt.p, dc.p, dpr.p, df.p, e->stream);
+  CU(cudaGetLastError());
+  if (n && tsdf_out) CU(cudaMemcpyAsync(tsdf_out, dt.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  if (n && rgbw) CU(cudaMemcpyAsync(rgbw, dc.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  if (n && prob) CU(cudaMemcpyAsync(prob, dpr.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  if (n && found) CU(cudaMemcpyAsync(found, df.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return TSDF_OK;
+}
+int tsdf_assign_voxels(tsdf_handle e, const int16_t* pts, int n, const float* tsdf_in, const uint8_t* rgbw, const float* prob) {
+  if (!e || !pts || n < 0) return fail(TSDF_E_INVALID, "bad argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e); if (rc) return rc;
+  DevBuf<short> dp; DevBuf<float> dt, dpr; DevBuf<unsigned> dc;
+  CU(dp.alloc(3 * (size_t)n)); CU(dt.alloc(n)); CU(dpr.alloc(n)); CU(dc.alloc(n));
+  if (n) CU(cudaMemcpyAsync(dp.p, pts, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
+  if (n && tsdf_in) CU(cudaMemcpyAsync(dt.p, tsdf_in, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  if (n && rgbw) CU(cudaMemcpyAsync(dc.p, rgbw, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  if (n && prob) CU(cudaMemcpyAsync(dpr.p, prob, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  launch_assign_list(e->S, dp.p, n, tsdf_in ? dt.p : nullptr, rgbw ? dc.p : nullptr, prob ? dpr.p : nullptr, e->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(e->stream));
+  return TSDF_OK;
+}
+
+int tsdf_export_blocks(tsdf_handle e, int16_t* keys, float* tsdf_out, uint8_t* rgbw, float* prob, int cap_blocks, int* n_blocks) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e); if (rc) return rc;
+  int n = 0;
+  rc = select_blocks(e, nullptr, &n);
+  if (rc) return rc;
+  if (n_blocks) *n_blocks = n;
+  const int m = std::min(n, cap_blocks);
+  if (m <= 0 || (!keys && !tsdf_out && !rgbw && !prob)) return TSDF_OK;
+  // download the first n blocks' keys to find the canonical order, then export in chunks
+  DevBuf<short> dk; CU(dk.alloc(3 * (size_t)n));
+  launch_export_blocks(e->S, e->selected, n, dk.p, nullptr, nullptr, nullptr, e->stream);
+  std::vector<short> hk(3 * (size_t)n);
+  CU(cudaMemcpyAsync(hk.data(), dk.p, sizeof(short) * hk.size(), cudaMemcpyDeviceToHost, e->stream));
+  std::vector<int> hsel(n);
+  CU(cudaMemcpyAsync(hsel.data(), e->selected, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    for (int c = 2; c >= 0; --c) if (hk[3 * a + c] != hk[3 * b + c]) return hk[3 * a + c] < hk[3 * b + c];
+    return false;
+  });
+  std::vector<int> sorted_sel(n);
+  for (int i = 0; i < n; ++i) sorted_sel[i] = hsel[order[i]];
+  CU(cudaMemcpyAsync(e->selected, sorted_sel.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  const int chunk = 4096;
+  DevBuf<short> ck; DevBuf<float> ct, cp; DevBuf<unsigned> cc;
+  CU(ck.alloc(3 * (size_t)chunk)); CU(ct.alloc((size_t)chunk * 512)); CU(cp.alloc((size_t)chunk * 512)); CU(cc.alloc((size_t)chunk * 512));
+  for (int b0 = 0; b0 < m; b0 += chunk) {
+    const int nb = std::min(chunk, m - b0);
+    launch_export_blocks(e->S, e->selected + b0, nb, ck.p, ct.p, cc.p, cp.p, e->stream);
+    CU(cudaGetLastError());
+    if (keys) CU(cudaMemcpyAsync(keys + 3 * (size_t)b0, ck.p, sizeof(short) * 3 * (size_t)nb, cudaMemcpyDeviceToHost, e->stream));
+    if (tsdf_out) CU(cudaMemcpyAsync(tsdf_out + (size_t)b0 * 512, ct.p, 4 * (size_t)nb * 512, cudaMemcpyDeviceToHost, e->stream));
+    if (rgbw) CU(cudaMemcpyAsync(rgbw + (size_t)b0 * 2048, cc.p, 4 * (size_t)nb * 512, cudaMemcpyDeviceToHost, e->stream));
+    if (prob) CU(cudaMemcpyAsync(prob + (size_t)b0 * 512, cp.p, 4 * (size_t)nb * 512, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  return TSDF_OK;
+}
+
+int tsdf_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaMallocHost(ptr, bytes));
+  return TSDF_OK;
+}
+int tsdf_host_free(void* ptr) { if (ptr) CU(cudaFreeHost(ptr)); return TSDF_OK; }
+
+int tsdf_set_profiling(tsdf_handle e, int enabled) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e); if (rc) return rc;
+  CU(cudaStreamSynchronize(e->copy_stream));
+  phase_collect(e);
+  e->profiling = enabled != 0;
+  for (int p = 0; p < PH_COUNT; ++p) { e->phase_total_ms[p] = 0.0; e->phase_count[p] = 0; }
+  e->totals = tsdf_counters{}; e->total_frames = 0;
+  return TSDF_OK;
+}
+int tsdf_get_phase_ms(tsdf_handle e, float out_ms[8], int64_t out_count[8]) {
+  if (!e || !out_ms) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e); if (rc) return rc;
+  CU(cudaStreamSynchronize(e->copy_stream));
+  phase_collect(e);
+  for (int p = 0; p < 8; ++p) { out_ms[p] = 0.f; if (out_count) out_count[p] = 0; }
+  for (int p = 0; p < PH_COUNT; ++p) { out_ms[p] = (float)e->phase_total_ms[p]; if (out_count) out_count[p] = e->phase_count[p]; }
+  return TSDF_OK;
+}
+int tsdf_get_totals(tsdf_handle e, tsdf_counters* sums, int64_t* n_frames) {
+  if (!e || !sums) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  *sums = e->totals;
+  if (n_frames) *n_frames = e->total_frames;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// tsdf_launch.h -- host-callable launchers of the engine's kernels (one per .cu file group).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tsdf_device.cuh"
+
+namespace tsdf {
+
+// kernels_integrate.cu
+void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const unsigned char* rgb, const float* depth,
+                           const float* ht, const float* lt, TexA* texA, TexB* texB, cudaStream_t st);
+void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int num_sms, cudaStream_t st);
+void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, const TexA* texA,
+                            const TexB* texB, int num_sms, cudaStream_t st);
+
+// kernels_raycast.cu
+void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, uchar4* rgba, uchar4* normal,
+                    float* hit_depth, unsigned long long* packed_keys, cudaStream_t st);
+
+// kernels_gather.cu
+struct GridBound { short xmin, xmax, ymin, ymax, zmin, zmax; };
+void launch_init_state(const DeviceState& S, cudaStream_t st);
+void launch_select_blocks(const DeviceState& S, bool use_bound, GridBound bound, int* selected, int num_sms,
+                          cudaStream_t st);
+void launch_download_voxels(const DeviceState& S, const int* selected, int n_selected, float voxel_size, float4* out,
+                            cudaStream_t st);
+void launch_export_blocks(const DeviceState& S, const int* selected, int n_selected, short* keys, float* tsdf,
+                          unsigned* rgbw, float* prob, cudaStream_t st);
+void launch_allocate_list(const DeviceState& S, const short* keys, int n, cudaStream_t st);
+void launch_delete_list(const DeviceState& S, const short* keys, int n, cudaStream_t st);
+void launch_retrieve_list(const DeviceState& S, const short* points, int n, float* tsdf, unsigned* rgbw, float* prob,
+                          int* found, cudaStream_t st);
+void launch_assign_list(const DeviceState& S, const short* points, int n, const float* tsdf, const unsigned* rgbw,
+                        const float* prob, cudaStream_t st);
+void launch_rehash(const DeviceState& S, int num_sms, cudaStream_t st);
+
+}  // namespace tsdf

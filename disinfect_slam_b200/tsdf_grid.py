@@ -1,0 +1,234 @@
+"""Python host mirror of the reference's `TSDFGrid` (utils/tsdf/voxel_tsdf.cuh:32-88) on top of the
+C ABI of libtsdf_b200.so.  Same method names and argument meaning as the reference class:
+
+    TSDFGrid(voxel_size, truncation)
+    Integrate(img_rgb, img_depth, img_ht, img_lt, max_depth, intrinsics, cam_T_world)
+    RayCast(max_depth, virtual_cam, cam_T_world) -> rgba, normal (+ hit depth)
+    GatherValid() / GatherVoxels(volumn) -> array of VoxelSpatialTSDF records (x, y, z, tsdf)
+
+numpy arrays stand in for cv::Mat, (fx, fy, cx, cy) for CameraIntrinsics<float>, and
+(q_xyzw, t_xyz) for SE3<float> (utils/cuda/lie_group.cuh:43-44).  The C++ shim with the
+reference's exact C++ signatures is include/tsdf_b200/voxel_tsdf.hpp.  No CPU fallback.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, Counters, TsdfError, check  # noqa: F401
+
+CameraParams = namedtuple("CameraParams", "intrinsics img_h img_w")  # utils/cuda/camera.cuh:54-68
+BoundingCube = namedtuple("BoundingCube", "xmin xmax ymin ymax zmin zmax")  # utils/tsdf/voxel_tsdf.cuh:12-19
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, n):
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    if a.size != n:
+        raise ValueError(f"expected {n} floats, got {a.size}")
+    return a
+
+
+def _pose(cam_T_world):
+    q, t = cam_T_world
+    return _f32(q, 4), _f32(t, 3)
+
+
+def hash_block(bx, by, bz):
+    """Hash() of the reference (utils/tsdf/voxel_hash.cu:31-35), through the C ABI."""
+    return int(_lib.lib().tsdf_hash(bx, by, bz))
+
+
+class PinnedArray:
+    """numpy view of pinned host memory from tsdf_host_alloc (DMA-able Integrate inputs)."""
+
+    def __init__(self, shape, dtype):
+        self.L = _lib.lib()
+        self.ptr = C.c_void_p()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        check(self.L.tsdf_host_alloc(C.byref(self.ptr), n))
+        buf = (C.c_char * n).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.L.tsdf_host_free(self.ptr)
+            self.ptr = None
+
+    __del__ = free
+
+
+class TSDFGrid:
+    def __init__(self, voxel_size, truncation, pool_blocks=None, table_slots=None, max_image_pixels=None, device=None,
+                 shard_rank=0, shard_count=1):
+        self.L = _lib.lib()
+        self.voxel_size, self.truncation = float(voxel_size), float(truncation)
+        cfg = Config()
+        check(self.L.tsdf_default_config(C.byref(cfg)))
+        if pool_blocks is not None:
+            cfg.pool_blocks = int(pool_blocks)
+        if table_slots is not None:
+            cfg.table_slots = int(table_slots)
+        elif pool_blocks is not None:
+            cfg.table_slots = max(1 << 16, 1 << int(np.ceil(np.log2(8 * cfg.pool_blocks))))
+        if max_image_pixels is not None:
+            cfg.max_image_pixels = int(max_image_pixels)
+        if device is not None:
+            cfg.device = int(device)
+        cfg.shard_rank, cfg.shard_count = int(shard_rank), int(shard_count)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        check(self.L.tsdf_create(voxel_size, truncation, C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tsdf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- TSDFGrid::Integrate (utils/tsdf/voxel_tsdf.cu:347-375) ------------------------------------
+    def _frame_args(self, img_rgb, img_depth, img_ht, img_lt, intrinsics, cam_T_world):
+        if img_rgb.dtype != np.uint8 or img_rgb.ndim != 3 or img_rgb.shape[2] != 3:
+            raise ValueError("img_rgb must be uint8 HxWx3 (CV_8UC3)")  # assert voxel_tsdf.cu:350
+        if img_depth.dtype != np.float32 or img_depth.ndim != 2:
+            raise ValueError("img_depth must be float32 HxW (CV_32FC1)")  # assert voxel_tsdf.cu:351
+        h, w = img_depth.shape
+        if img_rgb.shape[:2] != (h, w):
+            raise ValueError("rgb / depth size mismatch")  # asserts voxel_tsdf.cu:352-353
+        for a in (img_ht, img_lt):
+            if a.dtype != np.float32 or a.shape != (h, w):
+                raise ValueError("ht / lt must be float32 HxW")
+        for a in (img_rgb, img_depth, img_ht, img_lt):
+            if not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("images must be continuous")
+        q, t = _pose(cam_T_world)
+        return w, h, _f32(intrinsics, 4), q, t
+
+    def Integrate(self, img_rgb, img_depth, img_ht, img_lt, max_depth, intrinsics, cam_T_world, asynchronous=False):
+        w, h, K, q, t = self._frame_args(img_rgb, img_depth, img_ht, img_lt, intrinsics, cam_T_world)
+        fn = self.L.tsdf_integrate_async if asynchronous else self.L.tsdf_integrate
+        check(fn(self.h, _p(img_rgb), _p(img_depth), _p(img_ht), _p(img_lt), w, h, max_depth, _p(K), _p(q), _p(t)))
+
+    def IntegrateDevice(self, d_rgb, d_depth, d_ht, d_lt, width, height, max_depth, intrinsics, cam_T_world,
+                        after_event=None):
+        """Planes already in device memory (raw device pointers as ints)."""
+        q, t = _pose(cam_T_world)
+        K = _f32(intrinsics, 4)
+        check(self.L.tsdf_integrate_device(self.h, d_rgb, d_depth, d_ht, d_lt, width, height, max_depth, _p(K), _p(q),
+                                           _p(t), after_event))
+
+    # ---- TSDFGrid::RayCast (utils/tsdf/voxel_tsdf.cu:490-506) --------------------------------------
+    def RayCast(self, max_depth, virtual_cam, cam_T_world, want_depth=True):
+        K = _f32(virtual_cam.intrinsics, 4)
+        h, w = int(virtual_cam.img_h), int(virtual_cam.img_w)
+        q, t = _pose(cam_T_world)
+        rgba = np.empty((h, w, 4), np.uint8)
+        normal = np.empty((h, w, 4), np.uint8)
+        depth = np.empty((h, w), np.float32) if want_depth else None
+        check(self.L.tsdf_raycast(self.h, max_depth, w, h, _p(K), _p(q), _p(t), _p(rgba), _p(normal), _p(depth)))
+        return rgba, normal, depth
+
+    def RayCastDevice(self, max_depth, virtual_cam, cam_T_world, d_rgba=None, d_normal=None, d_depth=None,
+                      d_packed=None):
+        K = _f32(virtual_cam.intrinsics, 4)
+        q, t = _pose(cam_T_world)
+        check(self.L.tsdf_raycast_device(self.h, max_depth, int(virtual_cam.img_w), int(virtual_cam.img_h), _p(K),
+                                         _p(q), _p(t), d_rgba, d_normal, d_depth, d_packed))
+
+    # ---- TSDFGrid::GatherValid / GatherVoxels (utils/tsdf/voxel_tsdf.cu:399-454) -------------------
+    def _gather(self, bbox):
+        n = C.c_int64(0)
+        if bbox is None:
+            check(self.L.tsdf_gather_valid(self.h, None, 0, C.byref(n)))
+        else:
+            bb = _f32(bbox, 6)
+            check(self.L.tsdf_gather_in_bound(self.h, _p(bb), None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), np.float32)
+        if n.value:
+            check(self.L.tsdf_gather_fetch(self.h, _p(out), n.value))
+        return out
+
+    def GatherValid(self):
+        return self._gather(None)
+
+    def GatherVoxels(self, volumn):
+        return self._gather(tuple(volumn))
+
+    # ---- bookkeeping / parity access ---------------------------------------------------------------
+    def NumActiveBlock(self):  # VoxelHashTable::NumActiveBlock, voxel_hash.cu:200
+        n = C.c_int(0)
+        check(self.L.tsdf_num_active_blocks(self.h, C.byref(n)))
+        return n.value
+
+    def counters(self):
+        c = Counters()
+        check(self.L.tsdf_get_counters(self.h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in Counters._fields_ if k != "reserved"}
+
+    def synchronize(self):
+        check(self.L.tsdf_synchronize(self.h))
+
+    def stream(self):
+        return self.L.tsdf_stream(self.h)
+
+    def set_profiling(self, on=True):
+        check(self.L.tsdf_set_profiling(self.h, int(on)))
+
+    def phase_ms(self):
+        """Device ms per phase summed since set_profiling(True), and the number of timed launches."""
+        ms = np.zeros(8, np.float32)
+        cnt = np.zeros(8, np.int64)
+        check(self.L.tsdf_get_phase_ms(self.h, _p(ms), _p(cnt)))
+        names = ("upload", "allocate", "select", "integrate", "raycast", "gather")
+        return {n: float(ms[i]) for i, n in enumerate(names)}, {n: int(cnt[i]) for i, n in enumerate(names)}
+
+    def totals(self):
+        c = Counters()
+        n = C.c_int64(0)
+        check(self.L.tsdf_get_totals(self.h, C.byref(c), C.byref(n)))
+        d = {k: int(getattr(c, k)) for k, _ in Counters._fields_ if k != "reserved"}
+        d["frames"] = int(n.value)
+        return d
+
+    def allocate_blocks(self, keys):
+        keys = np.ascontiguousarray(keys, np.int16).reshape(-1, 3)
+        check(self.L.tsdf_allocate_blocks(self.h, _p(keys), len(keys)))
+
+    def delete_blocks(self, keys):
+        keys = np.ascontiguousarray(keys, np.int16).reshape(-1, 3)
+        check(self.L.tsdf_delete_blocks(self.h, _p(keys), len(keys)))
+
+    def retrieve(self, points):
+        pts = np.ascontiguousarray(points, np.int16).reshape(-1, 3)
+        n = len(pts)
+        tsdf, prob = np.empty(n, np.float32), np.empty(n, np.float32)
+        rgbw, found = np.empty((n, 4), np.uint8), np.empty(n, np.int32)
+        check(self.L.tsdf_retrieve_voxels(self.h, _p(pts), n, _p(tsdf), _p(rgbw), _p(prob), _p(found)))
+        return tsdf, rgbw, prob, found.astype(bool)
+
+    def assign(self, points, tsdf=None, rgbw=None, prob=None):
+        pts = np.ascontiguousarray(points, np.int16).reshape(-1, 3)
+        n = len(pts)
+        tsdf = None if tsdf is None else _f32(tsdf, n)
+        prob = None if prob is None else _f32(prob, n)
+        rgbw = None if rgbw is None else np.ascontiguousarray(rgbw, np.uint8).reshape(n, 4)
+        check(self.L.tsdf_assign_voxels(self.h, _p(pts), n, _p(tsdf), _p(rgbw), _p(prob)))
+
+    def export(self, voxels=True):
+        """All active blocks in canonical (z, y, x) order: keys, tsdf, rgbw, prob."""
+        n = C.c_int(0)
+        check(self.L.tsdf_export_blocks(self.h, None, None, None, None, 0, C.byref(n)))
+        nb = n.value
+        keys = np.zeros((nb, 3), np.int16)
+        tsdf = np.zeros((nb, 512), np.float32) if voxels else None
+        rgbw = np.zeros((nb, 512, 4), np.uint8) if voxels else None
+        prob = np.zeros((nb, 512), np.float32) if voxels else None
+        if nb:
+            check(self.L.tsdf_export_blocks(self.h, _p(keys), _p(tsdf), _p(rgbw), _p(prob), nb, C.byref(n)))
+        return keys, tsdf, rgbw, prob

@@ -1,0 +1,180 @@
+/*
+ * tsdf_b200.h -- C ABI of the B200-native voxel-hashed semantic TSDF engine (libtsdf_b200.so).
+ *
+ * This is the drop-in boundary for the reference's `TSDFGrid` class
+ * (utils/tsdf/voxel_tsdf.cuh:32-124 of yuzhou42/disinfect-slam).  The reference has no FFI
+ * layer -- its "operator API" is that C++ class -- so every entry point below names the
+ * member function (file:line relative to the reference root) it replaces.  Plain pointers and
+ * sizes only: no torch, Eigen or OpenCV types cross this boundary.  The C++17 shim that keeps
+ * the reference's own signatures on top of this ABI is include/tsdf_b200/voxel_tsdf.hpp.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative TSDF_E_* code otherwise;
+ *    tsdf_last_error() returns a thread-local description of the last failure.
+ *  - poses are cam_T_world as unit quaternion (x,y,z,w) + translation, exactly the storage of
+ *    SE3<float> (utils/cuda/lie_group.cuh:43-44); intrinsics are K = {fx, fy, cx, cy}
+ *    (utils/cuda/camera.cuh:12-17).
+ *  - images are row-major, continuous: rgb uint8 HxWx3 (RGB order), depth float32 metres,
+ *    ht / lt float32 probabilities (utils/tsdf/voxel_tsdf.cuh:47-59).
+ *  - the engine is not thread-safe (like TSDFGrid); callers serialise, but may call from any
+ *    host thread (the engine sets its CUDA device on entry).
+ *  - there is NO CPU fallback: every call needs the CUDA device chosen at tsdf_create.
+ */
+#ifndef TSDF_B200_H_
+#define TSDF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSDF_B200_ABI_VERSION 1
+
+enum {
+  TSDF_OK = 0,
+  TSDF_E_INVALID = -1,        /* bad argument (null pointer, size mismatch, image too large) */
+  TSDF_E_CUDA = -2,           /* CUDA runtime error; see tsdf_last_error() */
+  TSDF_E_POOL_EXHAUSTED = -3, /* block pool ran out (reference: device assert, voxel_mem.cu:39) */
+  TSDF_E_TABLE_FULL = -4,     /* hash table ran out of slots */
+  TSDF_E_NO_DEVICE = -5       /* no usable CUDA device: the engine never falls back to the CPU */
+};
+
+typedef struct tsdf_engine* tsdf_handle;
+
+/* Runtime replacements for the reference's compile-time #defines
+ * (NUM_BLOCK utils/tsdf/voxel_mem.cuh:11-12, NUM_ENTRY utils/tsdf/voxel_hash.cuh:13-25,
+ *  MAX_IMG_SIZE utils/tsdf/voxel_tsdf.cu:10-12). */
+typedef struct tsdf_config {
+  int32_t struct_size;      /* = sizeof(tsdf_config) */
+  int32_t device;           /* CUDA ordinal; -1 = current device */
+  int32_t pool_blocks;      /* 8^3-voxel blocks in the pool (default 1 << 18) */
+  int32_t table_slots;      /* open-addressing slots, power of two (default 1 << 21) */
+  int32_t max_image_pixels; /* largest W*H accepted (default 1920 * 1080) */
+  int32_t shard_rank;       /* multi-GPU block ownership: this engine keeps only blocks with */
+  int32_t shard_count;      /*   owner(block) == shard_rank of shard_count (default 0 of 1) */
+  int32_t flags;            /* reserved, 0 */
+} tsdf_config;
+
+/* Counters of the last tsdf_integrate* call (what the reference only logs through
+ * spdlog::debug, voxel_tsdf.cu:367,374,470). */
+typedef struct tsdf_counters {
+  int64_t n_active_pre;  /* active blocks before the frame */
+  int64_t n_new;         /* blocks allocated by this frame */
+  int64_t n_visible;     /* blocks that passed the any-corner visibility test */
+  int64_t n_updated;     /* voxel updates (voxels that passed every test in the integrate kernel) */
+  int64_t n_carved;      /* blocks freed by space carving */
+  int64_t n_active_post; /* active blocks after the frame */
+  int64_t n_candidates;  /* de-duplicated allocation requests probed in the table */
+  int64_t reserved;
+} tsdf_counters;
+
+const char* tsdf_last_error(void);
+int tsdf_abi_version(void);
+
+int tsdf_default_config(tsdf_config* cfg);
+
+/* TSDFGrid::TSDFGrid(voxel_size, truncation)            utils/tsdf/voxel_tsdf.cu:309-326
+ * + VoxelHashTable() / VoxelMemPool()                   utils/tsdf/voxel_hash.cu:37-45, voxel_mem.cu:13-27 */
+int tsdf_create(float voxel_size, float truncation, const tsdf_config* cfg /* may be NULL */, tsdf_handle* out);
+/* TSDFGrid::~TSDFGrid()                                 utils/tsdf/voxel_tsdf.cu:328-345 */
+int tsdf_destroy(tsdf_handle h);
+
+/* TSDFGrid::Integrate(rgb, depth, ht, lt, max_depth, intrinsics, cam_T_world)
+ *                                                       utils/tsdf/voxel_tsdf.cu:347-375
+ * Host buffers (pinned or pageable); synchronous like the reference: the buffers may be reused
+ * on return and the volume is up to date. */
+int tsdf_integrate(tsdf_handle h, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
+                   int width, int height, float max_depth, const float K[4], const float q_xyzw[4],
+                   const float t_xyz[3]);
+/* Pipelined variant: returns as soon as the host buffers have been consumed (copied to one of
+ * two device staging sets); the kernels of this frame overlap the next call's upload.  Call
+ * tsdf_synchronize() before reading counters / results.  Same arithmetic as tsdf_integrate. */
+int tsdf_integrate_async(tsdf_handle h, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
+                         int width, int height, float max_depth, const float K[4], const float q_xyzw[4],
+                         const float t_xyz[3]);
+/* Same, with the four planes already in device memory of the engine's GPU (SURVEY.md 8f rank 4:
+ * the segmentation net produces ht/lt on the GPU; multi-GPU ranks receive the broadcast frame
+ * in device memory).  Enqueues on the engine stream and returns without synchronising;
+ * `after_event` (cudaEvent_t or NULL) is waited on by the engine stream first. */
+int tsdf_integrate_device(tsdf_handle h, const void* d_rgb, const void* d_depth, const void* d_ht, const void* d_lt,
+                          int width, int height, float max_depth, const float K[4], const float q_xyzw[4],
+                          const float t_xyz[3], void* after_event);
+
+/* TSDFGrid::RayCast(max_depth, virtual_cam, cam_T_world, rgba, normal)
+ *                                                       utils/tsdf/voxel_tsdf.cu:490-506
+ * The reference writes two uchar4 images into GL textures; here they are copied to host memory
+ * (each pointer optional).  hit_depth (new, needed for multi-GPU nearest-hit compositing) is the
+ * camera-space z of the refined hit in metres, +inf where the ray misses. */
+int tsdf_raycast(tsdf_handle h, float max_depth, int width, int height, const float K[4], const float q_xyzw[4],
+                 const float t_xyz[3], uint8_t* rgba /* HxWx4 */, uint8_t* normal /* HxWx4 */,
+                 float* hit_depth /* HxW */);
+/* Device-output variant: results stay on the GPU (replacement for GLImage8UC4::LoadCuda,
+ * utils/gl/image.cc:108-119).  Pointers are device memory, each optional; if `packed_min_keys`
+ * is non-NULL it receives per ray two uint64 = (float_bits(hit_depth) << 32) | rgba / normal, the
+ * format used for nearest-hit min-compositing across GPUs.  Asynchronous on the engine stream. */
+int tsdf_raycast_device(tsdf_handle h, float max_depth, int width, int height, const float K[4],
+                        const float q_xyzw[4], const float t_xyz[3], void* d_rgba, void* d_normal,
+                        void* d_hit_depth, void* d_packed_min_keys);
+
+/* TSDFGrid::GatherValid()                               utils/tsdf/voxel_tsdf.cu:399-425
+ * TSDFGrid::GatherVoxels(BoundingCube<float>)           utils/tsdf/voxel_tsdf.cu:427-454
+ * out = array of VoxelSpatialTSDF {float x, y, z, tsdf} (utils/tsdf/voxel_types.cuh:48-57),
+ * 512 consecutive records per selected block in x + 8y + 64z order; block order is unspecified
+ * (hash-layout dependent in the reference too).  bbox = {xmin,xmax,ymin,ymax,zmin,zmax} metres,
+ * member order of BoundingCube (voxel_tsdf.cuh:12-19).  *n_voxels receives the number selected;
+ * at most cap_voxels are written; out == NULL only counts. */
+int tsdf_gather_valid(tsdf_handle h, float* out_xyzt, int64_t cap_voxels, int64_t* n_voxels);
+int tsdf_gather_in_bound(tsdf_handle h, const float bbox[6], float* out_xyzt, int64_t cap_voxels, int64_t* n_voxels);
+/* The gathers always leave their full result in an engine-owned device buffer (valid until the
+ * next gather): call with out_xyzt == NULL to learn *n_voxels, size the host array, then
+ * tsdf_gather_fetch() copies it without selecting again; or consume it on the GPU directly. */
+int tsdf_gather_fetch(tsdf_handle h, float* out_xyzt, int64_t cap_voxels);
+int tsdf_gather_device_result(tsdf_handle h, const void** d_out_xyzt, int64_t* n_voxels);
+
+/* VoxelHashTable::NumActiveBlock()                      utils/tsdf/voxel_hash.cu:200 */
+int tsdf_num_active_blocks(tsdf_handle h, int* n);
+int tsdf_get_counters(tsdf_handle h, tsdf_counters* out);
+int tsdf_synchronize(tsdf_handle h);
+/* cudaStream_t the engine enqueues on (for event interop with callers that own device data). */
+void* tsdf_stream(tsdf_handle h);
+
+/* Hash(block_pos) & BUCKET_MASK                         utils/tsdf/voxel_hash.cu:31-35
+ * (21-bit mask of the reference; the engine uses the same mix, masked to its own table size). */
+uint32_t tsdf_hash(int16_t bx, int16_t by, int16_t bz);
+
+/* Parity / unit-test access (what utils/tests/voxel_hash_test.cu:36-55 does with its own
+ * Allocate / Retrieve / Assignment kernels, and voxel_mem_test.cu with Aquire/Release).
+ * keys / points are int16 triples. */
+int tsdf_allocate_blocks(tsdf_handle h, const int16_t* block_keys, int n); /* VoxelHashTable::Allocate, voxel_hash.cu:58 */
+int tsdf_delete_blocks(tsdf_handle h, const int16_t* block_keys, int n);   /* VoxelHashTable::Delete,   voxel_hash.cu:122 */
+/* VoxelHashTable::Retrieve<T>, voxel_hash.cuh:104-113: absent -> tsdf 1, rgbw 0, prob 0, found 0 */
+int tsdf_retrieve_voxels(tsdf_handle h, const int16_t* points, int n, float* tsdf, uint8_t* rgbw /* n x 4 */,
+                         float* prob, int32_t* found);
+/* VoxelHashTable::RetrieveMutable + store, voxel_hash.cuh:124-161; any value pointer may be NULL */
+int tsdf_assign_voxels(tsdf_handle h, const int16_t* points, int n, const float* tsdf, const uint8_t* rgbw,
+                       const float* prob);
+/* All active blocks in canonical order (ascending z, y, x block coordinate): keys int16[n][3],
+ * tsdf float[n][512], rgbw uint8[n][512][4] (r,g,b,weight), prob float[n][512]; any may be NULL. */
+int tsdf_export_blocks(tsdf_handle h, int16_t* keys, float* tsdf, uint8_t* rgbw, float* prob, int cap_blocks,
+                       int* n_blocks);
+
+/* Pinned host memory helpers so callers can hand tsdf_integrate DMA-able buffers. */
+int tsdf_host_alloc(void** ptr, size_t bytes);
+int tsdf_host_free(void* ptr);
+
+/* Profiling.  While enabled, every phase is bracketed by CUDA events on the stream it is launched
+ * on and every retired frame's counters are summed; nothing synchronises until the getters run.
+ * tsdf_set_profiling() resets the sums.  out_ms = device milliseconds summed over all calls since
+ * then: [0] upload, [1] frame staging + allocate, [2] select visible, [3] integrate + carve,
+ * [4] raycast, [5] gather; out_count (optional) = number of timed launches per phase.
+ * tsdf_get_totals: sums of the per-frame counters and the number of frames. */
+int tsdf_set_profiling(tsdf_handle h, int enabled);
+int tsdf_get_phase_ms(tsdf_handle h, float out_ms[8], int64_t out_count[8]);
+int tsdf_get_totals(tsdf_handle h, tsdf_counters* sums, int64_t* n_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDF_B200_H_ */
