@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the voxel-hashed semantic TSDF hot path on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic input: for each of the
+`--streams` independent RGB-D streams resident on this GPU, one frame through
+TSDFGrid::Integrate followed by one TSDFGrid::RayCast from the same camera (BASELINE.json
+configs[1]: aligned 1280x720 L515/ZED-style frames, 5 mm voxels, "Integrate + RayCast every
+frame").  Several streams are interleaved per GPU so that the per-step working set (voxel blocks
++ frame planes of all streams) is larger than the 126 MB L2: no stream finds its blocks cached
+from its own previous frame, which is what the HBM roofline assumes.
+
+Legs (own arm):
+  value     frames already resident in HBM, tsdf_integrate_device + tsdf_raycast_device, CUDA
+            events bracketing exactly K steps, max over ranks
+  roofline  same frames on fresh engines with per-kernel CUDA events on the engine stream
+            (kernels serialised), achieved = algorithmic bytes / kernel time
+  e2e       host (pinned) buffers through tsdf_integrate + tsdf_raycast: H2D of every frame and
+            D2H of both rendered images + hit depth inside the timed region
+  cpu       the scalar/OpenMP CPU oracle on a bounded sample of the same workload (rank 0, N=1)
+
+`--impl reference` times the CPU oracle port of the reference path (the reference has no CPU
+implementation and its CUDA needs Eigen/OpenCV/GL) with all host threads.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from dataclasses import replace
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from disinfect_slam_b200 import synth  # noqa: E402
+
+L2_BYTES = 126e6
+METRIC, UNIT = "integrated_frames_per_s", "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--streams", type=int, default=4, help="independent RGB-D streams interleaved per GPU")
+    ap.add_argument("--lap", type=int, default=100, help="distinct frames per stream before the trajectory repeats")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scale", type=float, default=1.0, help="image scale (debug only; 1.0 = the named config)")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic frames (generated before CUDA is touched: the pool forks)
+# --------------------------------------------------------------------------------------------------
+def _gen_one(job):
+    cfg, i = job
+    f = synth.Scene(cfg).frame(i)
+    return f["rgb"], f["depth"], f["ht"], f["lt"], f["q"], f["t"], f["K"]
+
+
+def stream_cfg(cfg, rank, b):
+    return replace(cfg, seed=cfg.seed + 1000 * rank + 17 * b)
+
+
+def generate_streams(cfg, rank, n_streams, n_frames):
+    import multiprocessing as mp
+    jobs = [(stream_cfg(cfg, rank, b), i) for b in range(n_streams) for i in range(n_frames)]
+    procs = max(1, min(len(jobs), (os.cpu_count() or 2)))
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_gen_one, jobs, chunksize=1)
+    else:
+        res = [_gen_one(j) for j in jobs]
+    out = []
+    for b in range(n_streams):
+        fr = res[b * n_frames:(b + 1) * n_frames]
+        out.append(dict(rgb=[r[0] for r in fr], depth=[r[1] for r in fr], ht=[r[2] for r in fr], lt=[r[3] for r in fr],
+                        q=[r[4] for r in fr], t=[r[5] for r in fr], K=fr[0][6]))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (NVML polled from a thread while the GPU legs run)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples = []  # (t, sm_mhz, reasons_mask, power_w)
+        self.ok = False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # NVML missing: report it, never fake numbers
+            self.err = repr(e)
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), int(mhz), int(rs), pw))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.ok:
+            self.th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.th.join(timeout=1.0)
+
+    def summary(self, windows):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap,
+                 "hw_power_brake": nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown,
+                 "applications_clocks_setting": nv.nvmlClocksThrottleReasonApplicationsClocksSetting}
+        sel = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
+        where = "timed regions"
+        if len(sel) < 3:
+            sel, where = self.samples, "whole run (timed regions too short for >= 3 samples)"
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        mask = 0
+        for s in sel:
+            mask |= s[2]
+        return {"sm_mhz": statistics.median(s[1] for s in sel), "sm_max_mhz": self.max_mhz,
+                "reasons": [k for k, v in names.items() if mask & v], "samples": len(sel), "window": where,
+                "power_w_max": max(s[3] for s in sel)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle legs (cpu_baseline and --impl reference)
+# --------------------------------------------------------------------------------------------------
+def oracle_threads():
+    n = os.environ.get("OMP_NUM_THREADS")
+    return int(n) if n and n.isdigit() else (os.cpu_count() or 1)
+
+
+def oracle_step(o, cfg, st, i):
+    o.integrate(st["rgb"][i], st["depth"][i], st["ht"][i], st["lt"][i], cfg.max_depth, st["K"], st["q"][i], st["t"][i])
+    o.raycast(cfg.max_depth, cfg.width, cfg.height, st["K"], st["q"][i], st["t"][i])
+
+
+def cpu_sample(cfg, st, budget_s, max_frames):
+    """Oracle (C, -O2, OpenMP over blocks / rays) on the first frames of stream 0 until the budget is spent."""
+    from oracle.oracle import Oracle
+    o = Oracle(cfg.voxel_size, cfg.truncation)
+    n, t0 = 0, time.perf_counter()
+    while n < max_frames and (n < 2 or time.perf_counter() - t0 < budget_s):
+        oracle_step(o, cfg, st, n)
+        n += 1
+    dt = time.perf_counter() - t0
+    o.close()
+    return n / dt, n, dt
+
+
+def run_reference(args, cfg, rank, world):
+    """--impl reference: the oracle port on the host cores, one frame (Integrate + RayCast) per step."""
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    n_frames = min(args.lap, args.warmup + args.steps)
+    st = generate_streams(cfg, 0, 1, n_frames)[0]
+    o = Oracle(cfg.voxel_size, cfg.truncation)
+    for i in range(args.warmup):
+        oracle_step(o, cfg, st, i % n_frames)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        oracle_step(o, cfg, st, i % n_frames)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, 1, "one stream, one frame per step (bounded sample of the same workload)"),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": oracle_threads(), "kind": "port",
+                             "sample": f"{args.steps} frames (Integrate + RayCast each) of stream 0 after {args.warmup} warm-up frames; "
+                                       "oracle/tsdf_oracle.c -O2, OpenMP over visible blocks and image rows, allocation pass scalar"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference has no CPU TSDF path; its CUDA needs Eigen/OpenCV/GL (absent) -- see DESIGN.md"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, streams, extra):
+    return {"workload": f"{cfg.name}: Integrate + RayCast every frame; {extra}", "width": cfg.width, "height": cfg.height,
+            "voxel_size_m": cfg.voxel_size, "truncation_m": cfg.truncation, "max_depth_m": cfg.max_depth,
+            "block": "8^3 voxels", "streams_per_gpu": streams, "pool_blocks": cfg.pool_blocks}
+
+
+# --------------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = synth.config(args.workload)
+    if args.scale != 1.0:
+        cfg = cfg.scaled(args.scale)
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    B, K, W = args.streams, args.steps, args.warmup
+    n_frames = min(args.lap, W + K)
+    streams = generate_streams(cfg, rank, B, n_frames)  # before CUDA init (fork)
+
+    import torch
+    import torch.distributed as dist
+    from disinfect_slam_b200 import tsdf_grid
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, Wd = cfg.height, cfg.width
+    npx = H * Wd
+    cam = tsdf_grid.CameraParams(streams[0]["K"], H, Wd)
+
+    def make_engines():
+        return [tsdf_grid.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots,
+                                   max_image_pixels=npx, device=local_rank) for _ in range(B)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pinned host stacks (e2e inputs, and the source of the device-resident copies)
+    pinned = []
+    for st in streams:
+        p = {"rgb": tsdf_grid.PinnedArray((n_frames, H, Wd, 3), np.uint8), "depth": tsdf_grid.PinnedArray((n_frames, H, Wd), np.float32),
+             "ht": tsdf_grid.PinnedArray((n_frames, H, Wd), np.float32), "lt": tsdf_grid.PinnedArray((n_frames, H, Wd), np.float32)}
+        for k in p:
+            for i in range(n_frames):
+                p[k].array[i] = st[k][i]
+        pinned.append(p)
+    dres = [{k: torch.from_numpy(p[k].array).to(dev) for k in p} for p in pinned]
+    d_out = [dict(rgba=torch.empty((H, Wd, 4), dtype=torch.uint8, device=dev), normal=torch.empty((H, Wd, 4), dtype=torch.uint8, device=dev),
+                  depth=torch.empty((H, Wd), dtype=torch.float32, device=dev)) for _ in range(B)]
+    torch.cuda.synchronize()
+
+    def device_step(engs, i, serialise=False):
+        fi = i % n_frames
+        for b, g in enumerate(engs):
+            st, d = streams[b], dres[b]
+            pose = (st["q"][fi], st["t"][fi])
+            g.IntegrateDevice(d["rgb"][fi].data_ptr(), d["depth"][fi].data_ptr(), d["ht"][fi].data_ptr(), d["lt"][fi].data_ptr(),
+                              Wd, H, cfg.max_depth, st["K"], pose)
+            g.RayCastDevice(cfg.max_depth, cam, pose, d_out[b]["rgba"].data_ptr(), d_out[b]["normal"].data_ptr(),
+                            d_out[b]["depth"].data_ptr())
+            if serialise:
+                g.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    windows = []
+
+    # ---------------- leg 1: device-resident throughput (the `value`) ----------------
+    engs = make_engines()
+    ext = [torch.cuda.ExternalStream(g.stream(), device=dev) for g in engs]
+    for i in range(W):
+        device_step(engs, i)
+    for g in engs:
+        g.synchronize()
+        g.set_profiling(False)  # resets the counter totals
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream()
+    t_a = time.perf_counter()
+    ev0.record(cur)
+    for s in ext:
+        s.wait_event(ev0)
+    for i in range(W, W + K):
+        device_step(engs, i)
+    for s in ext:
+        e = torch.cuda.Event()
+        e.record(s)
+        cur.wait_event(e)
+    ev1.record(cur)
+    for g in engs:
+        g.synchronize()
+    torch.cuda.synchronize()
+    t_b = time.perf_counter()
+    windows.append((t_a, t_b))
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    barrier()
+    tot1 = [g.totals() for g in engs]
+    upd_local = sum(t["n_updated"] for t in tot1)
+    for g in engs:
+        g.close()
+    del engs, ext
+
+    # ---------------- leg 2: per-kernel times on the launching stream (roofline) ----------------
+    engs = make_engines()
+    for i in range(W):
+        device_step(engs, i, serialise=True)
+    for g in engs:
+        g.set_profiling(True)
+    t_a = time.perf_counter()
+    for i in range(W, W + K):
+        device_step(engs, i, serialise=True)
+    for g in engs:
+        g.synchronize()
+    t_b = time.perf_counter()
+    windows.append((t_a, t_b))
+    ph_ms, ph_n = {}, {}
+    tot = {}
+    for g in engs:
+        m, n = g.phase_ms()
+        for k in m:
+            ph_ms[k] = ph_ms.get(k, 0.0) + m[k]
+            ph_n[k] = ph_n.get(k, 0) + n[k]
+        for k, v in g.totals().items():
+            tot[k] = tot.get(k, 0) + v
+    for g in engs:
+        g.close()
+    del engs
+
+    # ---------------- leg 3: end to end through the host-buffer C ABI ----------------
+    e2e = None
+    if not args.no_e2e:
+        engs = make_engines()
+        houts = [(tsdf_grid.PinnedArray((H, Wd, 4), np.uint8), tsdf_grid.PinnedArray((H, Wd, 4), np.uint8),
+                  tsdf_grid.PinnedArray((H, Wd), np.float32)) for _ in range(B)]
+
+        def host_step(b, i):
+            fi = i % n_frames
+            g, p, st = engs[b], pinned[b], streams[b]
+            pose = (st["q"][fi], st["t"][fi])
+            g.Integrate(p["rgb"].array[fi], p["depth"].array[fi], p["ht"].array[fi], p["lt"].array[fi], cfg.max_depth, st["K"], pose)
+            g.RayCast(cfg.max_depth, cam, pose, out=tuple(a.array for a in houts[b]))
+
+        for i in range(W):
+            for b in range(B):
+                host_step(b, i)
+        barrier()
+        # one host thread per stream, each making the synchronous calls a TSDFSystem worker would make
+        start = threading.Barrier(B + 1)
+
+        def worker(b):
+            torch.cuda.set_device(local_rank)
+            start.wait()
+            for i in range(W, W + K):
+                host_step(b, i)
+
+        ths = [threading.Thread(target=worker, args=(b,)) for b in range(B)]
+        for t in ths:
+            t.start()
+        start.wait()
+        t_a = time.perf_counter()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize()
+        t_b = time.perf_counter()
+        windows.append((t_a, t_b))
+        e2e_s = t_b - t_a
+        if world > 1:
+            tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
+        e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * npx * B, "d2h_bytes_per_step": 12 * npx * B + 64 * B,
+               "api": "tsdf_integrate + tsdf_raycast (synchronous, pinned host buffers), one host thread per stream",
+               "ms_per_step": 1e3 * e2e_s / K}
+        for g in engs:
+            g.close()
+        del engs
+    sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- numbers ----------------
+    frames = world * B * K
+    value = frames / (ms * 1e-3)
+    upd_all = upd_local * world  # ranks run statistically identical streams; exact per-rank sums are rank-local
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    n_upd, n_vis, n_new, n_act = tot["n_updated"], tot["n_visible"], tot["n_new"], tot["n_active_pre"]
+    integ_bytes = 24 * n_upd + 4 * (512 * n_vis - n_upd)  # 24 B per voxel update + 4 B TSDF read of every other visible voxel
+    frame_bytes = 15 * npx * tot["frames"] + 8 * n_act + integ_bytes
+    integ_ms = ph_ms.get("integrate", 0.0)
+    launches = max(ph_n.get("integrate", 0), 1)
+    achieved = integ_bytes / (integ_ms * 1e-3) / 1e9 if integ_ms > 0 else 0.0
+    kern_total = sum(ph_ms.get(k, 0.0) for k in ("allocate", "select", "integrate", "raycast"))
+    kernels = {k: {"ms_per_launch": ph_ms[k] / max(ph_n[k], 1), "share_of_step_kernel_time": ph_ms[k] / kern_total if kern_total else 0.0}
+               for k in ("allocate", "select", "integrate", "raycast")}
+    ws = (n_vis * 6144 + 39 * npx * tot["frames"]) / max(K, 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(cfg, B, f"{B} independent streams interleaved per GPU, one frame of each per step"),
+                       frames_per_step=B * world, parallelism=f"replicas x{world} (independent streams, no data-path collective)",
+                       l2=f"inputs larger than L2: per-step working set {ws / 1e6:.0f} MB (visible voxel blocks + frame planes of {B} streams) vs 126 MB L2; no explicit flush"),
+        "voxel_updates_per_s": upd_all / (ms * 1e-3),
+        "voxel_updates_per_frame": n_upd / max(tot["frames"], 1),
+        "raycast_mrays_per_s": frames * npx / (ms * 1e-3) / 1e6,
+        "integrate_frame_hbm_gbs": frame_bytes / ((ph_ms.get("allocate", 0) + ph_ms.get("select", 0) + integ_ms) * 1e-3) / 1e9 if integ_ms else None,
+        "roofline": {"kernel": "integrate_carve_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": integ_bytes / launches, "us_per_launch": 1e3 * integ_ms / launches,
+                     "launches_timed": launches},
+        "kernels": kernels,
+        "e2e": e2e,
+        "gpu_launches": 4 * B * K,
+        "clocks": sampler.summary(windows[:1]),
+        "counters_per_frame": {k: tot[k] / max(tot["frames"], 1) for k in ("n_new", "n_visible", "n_updated", "n_carved", "n_active_post")},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, n, dt = cpu_sample(cfg, streams[0], args.cpu_seconds, n_frames)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": oracle_threads(), "kind": "port",
+                                "sample": f"first {n} frames of stream 0 (Integrate + RayCast each), {dt:.1f} s; oracle/tsdf_oracle.c -O2, "
+                                          "OpenMP over visible blocks and image rows, allocation pass scalar"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -162,7 +162,7 @@ static int retire_slot(tsdf_engine* e, int s) {
   k.n_active_post = e->cfg.pool_blocks - c[C_FREE];
   e->last = k;
   e->n_active = (int)k.n_active_post;
-  if (e->profiling) {
+  {  // sums since the last tsdf_set_profiling() call, kept whether or not phase timing is on
     e->totals.n_new += k.n_new; e->totals.n_visible += k.n_visible; e->totals.n_updated += k.n_updated;
     e->totals.n_carved += k.n_carved; e->totals.n_candidates += k.n_candidates;
     e->totals.n_active_post += k.n_active_post; e->totals.n_active_pre += k.n_active_pre;

@@ -124,13 +124,20 @@ class TSDFGrid:
                                            _p(t), after_event))
 
     # ---- TSDFGrid::RayCast (utils/tsdf/voxel_tsdf.cu:490-506) --------------------------------------
-    def RayCast(self, max_depth, virtual_cam, cam_T_world, want_depth=True):
+    def RayCast(self, max_depth, virtual_cam, cam_T_world, want_depth=True, out=None):
+        """`out` = optional (rgba, normal, depth) host arrays to fill (e.g. PinnedArray views)."""
         K = _f32(virtual_cam.intrinsics, 4)
         h, w = int(virtual_cam.img_h), int(virtual_cam.img_w)
         q, t = _pose(cam_T_world)
-        rgba = np.empty((h, w, 4), np.uint8)
-        normal = np.empty((h, w, 4), np.uint8)
-        depth = np.empty((h, w), np.float32) if want_depth else None
+        if out is not None:
+            rgba, normal, depth = out
+            for a, shp, dt in ((rgba, (h, w, 4), np.uint8), (normal, (h, w, 4), np.uint8), (depth, (h, w), np.float32)):
+                if a is not None and (a.shape != shp or a.dtype != dt or not a.flags["C_CONTIGUOUS"]):
+                    raise ValueError("RayCast out buffers must be contiguous rgba/normal uint8 HxWx4, depth float32 HxW")
+        else:
+            rgba = np.empty((h, w, 4), np.uint8)
+            normal = np.empty((h, w, 4), np.uint8)
+            depth = np.empty((h, w), np.float32) if want_depth else None
         check(self.L.tsdf_raycast(self.h, max_depth, w, h, _p(K), _p(q), _p(t), _p(rgba), _p(normal), _p(depth)))
         return rgba, normal, depth
 

@@ -165,8 +165,8 @@ int tsdf_host_alloc(void** ptr, size_t bytes);
 int tsdf_host_free(void* ptr);
 
 /* Profiling.  While enabled, every phase is bracketed by CUDA events on the stream it is launched
- * on and every retired frame's counters are summed; nothing synchronises until the getters run.
- * tsdf_set_profiling() resets the sums.  out_ms = device milliseconds summed over all calls since
+ * on; nothing synchronises until the getters run.  Every retired frame's counters are summed
+ * (profiling on or off); tsdf_set_profiling() resets the sums.  out_ms = device milliseconds summed over all calls since
  * then: [0] upload, [1] frame staging + allocate, [2] select visible, [3] integrate + carve,
  * [4] raycast, [5] gather; out_count (optional) = number of timed launches per phase.
  * tsdf_get_totals: sums of the per-frame counters and the number of frames. */
