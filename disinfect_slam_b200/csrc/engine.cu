@@ -51,9 +51,11 @@ struct tsdf_engine {
   int cur = 0;
   int last_slot = -1;  // slot of the most recent frame (its counters are the "last" ones)
   int* visible = nullptr; int* selected = nullptr;
+  SkipMap skip{};                    // RayCast empty-space skip map, rebuilt when the block set changed
+  uint64_t volume_epoch = 1, skip_epoch = 0;
   uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
   float4* gather_out = nullptr; size_t gather_cap = 0; int64_t gather_n = 0;
-  int* h_scalar = nullptr;  // pinned scratch (16 ints)
+  int* h_scalar = nullptr;  // pinned scratch (C_COUNT ints)
   int n_active = 0;         // host mirror after the last completed frame
   tsdf_counters last{};
   bool profiling = false;
@@ -133,7 +135,7 @@ static int check_frame_args(tsdf_engine* e, const void* a, const void* b, const 
 // kernels of one frame, enqueued on the compute stream; no host synchronisation
 static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned char* rgb, const float* depth,
                           const float* ht, const float* lt, FrameBuf& f) {
-  cudaMemsetAsync(e->S.ctr + C_NVIS, 0, sizeof(int) * (C_COUNT - C_NVIS), e->stream);
+  cudaMemsetAsync(e->S.ctr + C_PER_CALL, 0, sizeof(int) * (C_COUNT - C_PER_CALL), e->stream);
   phase_begin(e, PH_ALLOC, e->stream);
   launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.texA, f.texB, e->stream);
   phase_end(e, PH_ALLOC, e->stream);
@@ -146,6 +148,7 @@ static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned c
   cudaMemcpyAsync(f.h_ctr, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream);
   cudaEventRecord(f.done, e->stream);
   f.in_flight = true;
+  e->volume_epoch++;
 }
 
 // wait for the frame that used slot `s`, fold its counters into the host mirror, surface errors
@@ -248,6 +251,8 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   CUX(cudaMalloc(&S.ctr, sizeof(int) * C_COUNT));
   CUX(cudaMalloc(&e->visible, sizeof(int) * (size_t)cfg.pool_blocks));
   CUX(cudaMalloc(&e->selected, sizeof(int) * (size_t)cfg.pool_blocks));
+  CUX(cudaMalloc(&e->skip.dist, kSkipMaxCells)); CUX(cudaMalloc(&e->skip.scratch, kSkipMaxCells));
+  CUX(cudaMalloc(&e->skip.hdr, sizeof(int) * 8));
   const size_t npx = (size_t)cfg.max_image_pixels;
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
@@ -259,7 +264,7 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
     memset(f.h_ctr, 0, sizeof(int) * C_COUNT);
   }
   CUX(cudaMalloc(&e->rgba, sizeof(uchar4) * npx)); CUX(cudaMalloc(&e->normal, sizeof(uchar4) * npx)); CUX(cudaMalloc(&e->hit_depth, sizeof(float) * npx));
-  CUX(cudaMallocHost(&e->h_scalar, sizeof(int) * 16));
+  CUX(cudaMallocHost(&e->h_scalar, sizeof(int) * C_COUNT));
   launch_init_state(S, e->stream);
   CUX(cudaGetLastError());
   CUX(cudaStreamSynchronize(e->stream));
@@ -275,6 +280,7 @@ int tsdf_destroy(tsdf_handle e) {
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
   cudaFree(e->visible); cudaFree(e->selected);
+  cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr);
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
     cudaFree(f.rgb); cudaFree(f.depth); cudaFree(f.ht); cudaFree(f.lt); cudaFree(f.texA); cudaFree(f.texB);
@@ -362,7 +368,11 @@ int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const floa
   CU(cudaSetDevice(e->device));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
   phase_begin(e, PH_RAYCAST, e->stream);
-  launch_raycast(e->S, P, e->truncation / 2, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
+  if (e->skip_epoch != e->volume_epoch) {  // block set may have changed since the map was built
+    launch_build_skip_map(e->S, e->skip, e->num_sms, e->stream);
+    e->skip_epoch = e->volume_epoch;
+  }
+  launch_raycast(e->S, P, e->truncation / 2, e->skip, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
                  (unsigned long long*)d_packed, e->stream);  // step = truncation / 2, voxel_tsdf.cu:497
   phase_end(e, PH_RAYCAST, e->stream);
   CU(cudaGetLastError());
@@ -486,6 +496,7 @@ int tsdf_allocate_blocks(tsdf_handle e, const int16_t* keys, int n) {
   DevBuf<short> d; CU(d.alloc(3 * (size_t)n));
   if (n) CU(cudaMemcpyAsync(d.p, keys, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
   launch_allocate_list(e->S, d.p, n, e->stream);
+  e->volume_epoch++;
   return after_mutation(e);
 }
 int tsdf_delete_blocks(tsdf_handle e, const int16_t* keys, int n) {
@@ -495,6 +506,7 @@ int tsdf_delete_blocks(tsdf_handle e, const int16_t* keys, int n) {
   DevBuf<short> d; CU(d.alloc(3 * (size_t)n));
   if (n) CU(cudaMemcpyAsync(d.p, keys, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
   launch_delete_list(e->S, d.p, n, e->stream);
+  e->volume_epoch++;
   return after_mutation(e);
 }
 int tsdf_retrieve_voxels(tsdf_handle e, const int16_t* pts, int n, float* tsdf_out, uint8_t* rgbw, float* prob, int32_t* found) {

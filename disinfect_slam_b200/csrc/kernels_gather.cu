@@ -22,7 +22,10 @@ __global__ void init_state_kernel(DeviceState S) {
     S.block_key[i] = kEmpty;
     S.free_stack[i] = S.pool_blocks - 1 - (int)i;
   }
-  if (blockIdx.x == 0 && threadIdx.x < C_COUNT) S.ctr[threadIdx.x] = (threadIdx.x == C_FREE) ? S.pool_blocks : 0;
+  if (blockIdx.x == 0 && threadIdx.x < C_COUNT) {
+    const int c = threadIdx.x;
+    S.ctr[c] = c == C_FREE ? S.pool_blocks : (c >= C_MIN_X && c <= C_MIN_Z) ? 0x7FFFFFFF : (c >= C_MAX_X && c <= C_MAX_Z) ? -0x7FFFFFFF : 0;
+  }
 }
 
 // check_valid_kernel / check_bound_kernel (voxel_tsdf.cu:14-32) + compaction

@@ -4,9 +4,17 @@
 // (step = truncation / 2), nearest-voxel lookups with a per-thread block cache (including the
 // reference's negative cache for absent blocks, voxel_hash.cuh:124-161), sign-change hit test,
 // bisection refinement, central-difference normal, Lambert shading and the semantic overlay.
-// The sample positions are accumulated exactly like the reference (pos += step, float32, no FMA)
-// so the hit decisions are bit-identical.  New output: per-ray hit depth (camera z, metres) and
-// a packed (depth_bits << 32 | colour) key for nearest-hit min-compositing across GPUs.
+//
+// The sample positions are accumulated exactly like the reference (pos += step, float32, no FMA),
+// so every sample the reference takes is taken at the bit-identical position here.  What is new is
+// that samples which provably land in unallocated space are not looked up at all: a dense
+// Chebyshev-distance map over the cells of the active-block AABB (built on the GPU whenever the
+// block set changed, ~1 byte per 8^3..(8<<shift)^3 voxels, L1/L2 resident) says how many of the
+// following samples cannot reach an allocated block; those samples only advance the position.
+// Unallocated space reads TSDF = +1 in the reference (VoxelTSDF(), voxel_types.cu:8) and a +1
+// sample can neither start nor complete a hit (voxel_tsdf.cu:260), so the result is identical.
+// New output: per-ray hit depth (camera z, metres) and a packed (depth_bits << 32 | colour) key
+// for nearest-hit min-compositing across GPUs.
 #include <math_constants.h>
 
 #include "tsdf_device.cuh"
@@ -14,32 +22,144 @@
 
 namespace tsdf {
 
+// ------------------------------------------------------------------------------------------
+// skip-map construction (all sizes live on the device: no host round trip)
+// ------------------------------------------------------------------------------------------
+__global__ void skip_prepare_kernel(DeviceState S, SkipMap M) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int x0 = S.ctr[C_MIN_X], y0 = S.ctr[C_MIN_Y], z0 = S.ctr[C_MIN_Z];
+  const int x1 = S.ctr[C_MAX_X], y1 = S.ctr[C_MAX_Y], z1 = S.ctr[C_MAX_Z];
+  int* h = M.hdr;
+  if (x1 < x0) { h[0] = h[1] = h[2] = 0; h[3] = h[4] = h[5] = 0; h[6] = 0; h[7] = 0; return; }
+  int shift = 0;
+  long long nx, ny, nz;
+  for (;; ++shift) {
+    nx = ((x1 - x0) >> shift) + 1; ny = ((y1 - y0) >> shift) + 1; nz = ((z1 - z0) >> shift) + 1;
+    if (nx * ny * nz <= (long long)kSkipMaxCells) break;
+  }
+  h[0] = x0; h[1] = y0; h[2] = z0; h[3] = (int)nx; h[4] = (int)ny; h[5] = (int)nz; h[6] = shift; h[7] = (int)(nx * ny * nz);
+}
+
+__global__ void __launch_bounds__(256) skip_fill_kernel(SkipMap M) {
+  const int n = M.hdr[7];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) M.dist[i] = kSkipCap;
+}
+
+__global__ void __launch_bounds__(256) skip_mark_kernel(DeviceState S, SkipMap M) {
+  const int hw = S.ctr[C_HIGH_WATER];
+  const int ox = M.hdr[0], oy = M.hdr[1], oz = M.hdr[2], nx = M.hdr[3], ny = M.hdr[4], shift = M.hdr[6];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    const u64 k = S.block_key[i];
+    if (k == kEmpty) continue;
+    int bx, by, bz; unpack_key(k, bx, by, bz);
+    const int cx = (bx - ox) >> shift, cy = (by - oy) >> shift, cz = (bz - oz) >> shift;
+    M.dist[((size_t)cz * ny + cy) * nx + cx] = 0;
+  }
+}
+
+// one separable pass of the capped Chebyshev distance transform along `axis`:
+//   out(c) = min_k max(in(c +- k e_axis), k)
+__global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigned char* __restrict__ in,
+                                                        unsigned char* __restrict__ out, int axis) {
+  const int nx = M.hdr[3], ny = M.hdr[4], nz = M.hdr[5], n = M.hdr[7];
+  const int len = axis == 0 ? nx : axis == 1 ? ny : nz;
+  const int stride = axis == 0 ? 1 : axis == 1 ? nx : nx * ny;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int cx = i % nx, cy = (i / nx) % ny, cz = i / (nx * ny);
+    const int c = axis == 0 ? cx : axis == 1 ? cy : cz;
+    int best = in[i];
+    for (int k = 1; k < best; ++k) {
+      if (c - k >= 0) best = min(best, max((int)in[i - k * stride], k));
+      if (c + k < len) best = min(best, max((int)in[i + k * stride], k));
+    }
+    out[i] = (unsigned char)best;
+  }
+}
+
+void launch_build_skip_map(const DeviceState& S, const SkipMap& M, int num_sms, cudaStream_t st) {
+  skip_prepare_kernel<<<1, 32, 0, st>>>(S, M);
+  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(M);
+  skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(S, M);
+  skip_pass_kernel<<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, 0);
+  skip_pass_kernel<<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist, 1);
+  skip_pass_kernel<<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, 2);
+  // result is in M.scratch; the raycast kernel is launched with the two pointers swapped
+}
+
+// ------------------------------------------------------------------------------------------
+// ray march
+// ------------------------------------------------------------------------------------------
+struct Grid { int ox, oy, oz, nx, ny, nz, shift; const unsigned char* dist; };
 struct BlockCache { u64 key; int idx; };
 
-__device__ __forceinline__ void cache_lookup(const DeviceState& S, BlockCache& c, int px, int py, int pz) {
-  const u64 key = pack_key(px >> 3, py >> 3, pz >> 3);
-  if (key != c.key) { c.key = key; c.idx = table_find(S, key); }
+// Chebyshev distance (cells) from block (bx,by,bz) to the nearest cell holding an active block;
+// 0 = this cell holds one (the block itself may still be absent when shift > 0)
+__device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int bz) {
+  const int cx = (bx - G.ox) >> G.shift, cy = (by - G.oy) >> G.shift, cz = (bz - G.oz) >> G.shift;
+  if ((unsigned)cx < (unsigned)G.nx && (unsigned)cy < (unsigned)G.ny && (unsigned)cz < (unsigned)G.nz)
+    return __ldg(G.dist + ((size_t)cz * G.ny + cy) * G.nx + cx);
+  // outside the AABB: the gap to the box (in cells) is a lower bound of the distance
+  const int gx = cx < 0 ? -cx : (cx >= G.nx ? cx - G.nx + 1 : 0);
+  const int gy = cy < 0 ? -cy : (cy >= G.ny ? cy - G.ny + 1 : 0);
+  const int gz = cz < 0 ? -cz : (cz >= G.nz ? cz - G.nz + 1 : 0);
+  return max(gx, max(gy, gz));
+}
+
+__device__ __forceinline__ void cache_lookup(const DeviceState& S, const Grid& G, BlockCache& c, int px, int py, int pz) {
+  const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
+  const u64 key = pack_key(bx, by, bz);
+  if (key != c.key) { c.key = key; c.idx = cell_distance(G, bx, by, bz) == 0 ? table_find(S, key) : -1; }
 }
 // Retrieve<VoxelTSDF>: absent -> VoxelTSDF() == +1 (voxel_types.cu:8)
-__device__ __forceinline__ float fetch_tsdf(const DeviceState& S, BlockCache& c, int px, int py, int pz) {
-  cache_lookup(S, c, px, py, pz);
+__device__ __forceinline__ float fetch_tsdf(const DeviceState& S, const Grid& G, BlockCache& c, int px, int py, int pz) {
+  cache_lookup(S, G, c, px, py, pz);
   if (c.idx < 0) return 1.f;
   return __ldg(block_tsdf(S, c.idx) + voxel_index(px, py, pz));
 }
-__device__ __forceinline__ float fetch_tsdf_f(const DeviceState& S, BlockCache& c, float3 p) {
-  return fetch_tsdf(S, c, round_to_voxel(p.x), round_to_voxel(p.y), round_to_voxel(p.z));
+__device__ __forceinline__ float fetch_tsdf_f(const DeviceState& S, const Grid& G, BlockCache& c, float3 p) {
+  return fetch_tsdf(S, G, c, round_to_voxel(p.x), round_to_voxel(p.y), round_to_voxel(p.z));
+}
+
+// One march sample: TSDF at the voxel nearest to p and `skip` = how many of the FOLLOWING samples are
+// guaranteed to land in unallocated space.  With d = distance of p's cell and cs voxels per cell,
+// every voxel within Chebyshev radius (d-1)*cs of p is unallocated; m further steps move the rounded
+// voxel by at most m*smax + 1 (+1 slack for float accumulation), so m = floor(((d-1)*cs - 2) / smax).
+__device__ __forceinline__ float march_sample(const DeviceState& S, const Grid& G, BlockCache& c, float3 p,
+                                              float inv_smax, int& skip) {
+  const int px = round_to_voxel(p.x), py = round_to_voxel(p.y), pz = round_to_voxel(p.z);
+  const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
+  const u64 key = pack_key(bx, by, bz);
+  skip = 0;
+  if (key != c.key) {
+    c.key = key;
+    const int d = cell_distance(G, bx, by, bz);
+    if (d == 0) {
+      c.idx = table_find(S, key);
+    } else {
+      c.idx = -1;
+      if (d >= 2) skip = __float2int_rd((float)(((d - 1) << (3 + G.shift)) - 2) * inv_smax);
+      return 1.f;
+    }
+  }
+  if (c.idx < 0) return 1.f;
+  return __ldg(block_tsdf(S, c.idx) + voxel_index(px, py, pz));
 }
 
 __device__ __forceinline__ unsigned char f2u8(float f) { return (unsigned char)min(255, max(0, __float2int_rz(f))); }
+__device__ __forceinline__ float3 add3(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 
-__global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams P, float step_size,
+__global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams P, float step_size, SkipMap M,
                                                       uchar4* __restrict__ img_rgba, uchar4* __restrict__ img_normal,
                                                       float* __restrict__ img_depth, u64* __restrict__ packed) {
-  // 16x16 pixel tiles: neighbouring rays walk the same blocks (L1 reuse of table slots and voxels)
-  const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-  const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+  // CTA = 32 x 8 pixels, warp = 8 x 4 pixels: neighbouring rays walk the same cells and blocks
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+  const int y = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
   if (x >= P.w || y >= P.h) return;
   const int idx = y * P.w + x;
+  Grid G;
+  G.ox = M.hdr[0]; G.oy = M.hdr[1]; G.oz = M.hdr[2]; G.nx = M.hdr[3]; G.ny = M.hdr[4]; G.nz = M.hdr[5]; G.shift = M.hdr[6];
+  G.dist = M.dist;
 
   // voxel_tsdf.cu:243-250
   const float3 pos_cam = kmul(P.Kinv, f3((float)x, (float)y, 1.f));
@@ -51,16 +171,28 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
                                   ray_dir_world.z * step_size / P.voxel_size);
   const int max_step = __float2int_rz(ceilf(P.max_depth / step_size));
   float3 pos_grid = f3(P.world_T_cam.tx / P.voxel_size, P.world_T_cam.ty / P.voxel_size, P.world_T_cam.tz / P.voxel_size);
+  // conservative 1 / (largest per-step voxel displacement); only used to size skips
+  const float smax = fmaxf(fmaxf(fabsf(ray_step_grid.x), fabsf(ray_step_grid.y)), fabsf(ray_step_grid.z));
+  const float inv_smax = 1.f / (smax * 1.001f + 1e-6f);
 
   BlockCache cache; cache.key = kEmpty; cache.idx = -1;
-  float tsdf_prev = fetch_tsdf_f(S, cache, pos_grid);
-  pos_grid = f3(pos_grid.x + ray_step_grid.x, pos_grid.y + ray_step_grid.y, pos_grid.z + ray_step_grid.z);
+  int skip;
+  float tsdf_prev = march_sample(S, G, cache, pos_grid, inv_smax, skip);
+  pos_grid = add3(pos_grid, ray_step_grid);
+  int i = 1;
 
   uchar4 out_rgba = make_uchar4(0, 0, 0, 0), out_normal = make_uchar4(0, 0, 0, 0);
   float out_depth = CUDART_INF_F;
 
-  for (int i = 1; i < max_step; ++i) {
-    const float tsdf_curr = fetch_tsdf_f(S, cache, pos_grid);
+  for (;;) {
+    if (skip > 0) {  // the next `skip` samples read +1: advance the position exactly as the reference does
+      const int k = min(skip, max_step - i);
+#pragma unroll 4
+      for (int j = 0; j < k; ++j) pos_grid = add3(pos_grid, ray_step_grid);
+      i += k;
+    }
+    if (i >= max_step) break;
+    const float tsdf_curr = march_sample(S, G, cache, pos_grid, inv_smax, skip);
     // ray hit front surface (voxel_tsdf.cu:260)
     if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) {
       float3 pos1 = f3(pos_grid.x - ray_step_grid.x, pos_grid.y - ray_step_grid.y, pos_grid.z - ray_step_grid.z);
@@ -70,12 +202,12 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
       for (;;) {
         const float3 dd = f3(pos1.x - pos2.x, pos1.y - pos2.y, pos1.z - pos2.z);
         if (!(dot3(dd, dd) >= 0.1f)) break;
-        const float tm = fetch_tsdf_f(S, cache, mid);
+        const float tm = fetch_tsdf_f(S, G, cache, mid);
         if (tm < 0) pos2 = mid; else pos1 = mid;
         mid = f3((pos1.x + pos2.x) / 2.f, (pos1.y + pos2.y) / 2.f, (pos1.z + pos2.z) / 2.f);
       }
       const int fx = round_to_voxel(mid.x), fy = round_to_voxel(mid.y), fz = round_to_voxel(mid.z);
-      cache_lookup(S, cache, fx, fy, fz);
+      cache_lookup(S, G, cache, fx, fy, fz);
       uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
       float prob = 0.f;
       if (cache.idx >= 0) {
@@ -84,9 +216,9 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
         prob = logit_to_prob(__ldg(block_logit(S, cache.idx) + k));
       }
       // central differences on nearest voxels (voxel_tsdf.cu:280-291); short arithmetic wraps like the reference
-      const float gxp = fetch_tsdf(S, cache, (short)(fx + 1), fy, fz), gxn = fetch_tsdf(S, cache, (short)(fx - 1), fy, fz);
-      const float gyp = fetch_tsdf(S, cache, fx, (short)(fy + 1), fz), gyn = fetch_tsdf(S, cache, fx, (short)(fy - 1), fz);
-      const float gzp = fetch_tsdf(S, cache, fx, fy, (short)(fz + 1)), gzn = fetch_tsdf(S, cache, fx, fy, (short)(fz - 1));
+      const float gxp = fetch_tsdf(S, G, cache, (short)(fx + 1), fy, fz), gxn = fetch_tsdf(S, G, cache, (short)(fx - 1), fy, fz);
+      const float gyp = fetch_tsdf(S, G, cache, fx, (short)(fy + 1), fz), gyn = fetch_tsdf(S, G, cache, fx, (short)(fy - 1), fz);
+      const float gzp = fetch_tsdf(S, G, cache, fx, fy, (short)(fz + 1)), gzn = fetch_tsdf(S, G, cache, fx, fy, (short)(fz - 1));
       const float3 nrm = f3(gxp - gxn, gyp - gyn, gzp - gzn);
       const float3 neg_dir = f3(-ray_dir_world.x, -ray_dir_world.y, -ray_dir_world.z);
       const float diffusivity = fmaxf(dot3(nrm, neg_dir) / sqrtf(sqnorm3(nrm)), 0);
@@ -100,7 +232,8 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
       break;
     }
     tsdf_prev = tsdf_curr;
-    pos_grid = f3(pos_grid.x + ray_step_grid.x, pos_grid.y + ray_step_grid.y, pos_grid.z + ray_step_grid.z);
+    pos_grid = add3(pos_grid, ray_step_grid);
+    ++i;
   }
 
   if (img_rgba) img_rgba[idx] = out_rgba;
@@ -114,10 +247,12 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
   }
 }
 
-void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, uchar4* rgba, uchar4* normal,
-                    float* hit_depth, unsigned long long* packed_keys, cudaStream_t st) {
-  dim3 grid((P.w + 15) / 16, (P.h + 15) / 16);
-  raycast_kernel<<<grid, 256, 0, st>>>(S, P, step_size, rgba, normal, hit_depth, packed_keys);
+void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, const SkipMap& M, uchar4* rgba,
+                    uchar4* normal, float* hit_depth, unsigned long long* packed_keys, cudaStream_t st) {
+  dim3 grid((P.w + 31) / 32, (P.h + 7) / 8);
+  SkipMap R = M;  // launch_build_skip_map leaves the final distances in `scratch`
+  R.dist = M.scratch; R.scratch = M.dist;
+  raycast_kernel<<<grid, 256, 0, st>>>(S, P, step_size, R, rgba, normal, hit_depth, packed_keys);
 }
 
 }  // namespace tsdf

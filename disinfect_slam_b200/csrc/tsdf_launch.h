@@ -14,8 +14,9 @@ void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const in
                             const TexB* texB, int num_sms, cudaStream_t st);
 
 // kernels_raycast.cu
-void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, uchar4* rgba, uchar4* normal,
-                    float* hit_depth, unsigned long long* packed_keys, cudaStream_t st);
+void launch_build_skip_map(const DeviceState& S, const SkipMap& M, int num_sms, cudaStream_t st);
+void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, const SkipMap& M, uchar4* rgba,
+                    uchar4* normal, float* hit_depth, unsigned long long* packed_keys, cudaStream_t st);
 
 // kernels_gather.cu
 struct GridBound { short xmin, xmax, ymin, ymax, zmin, zmax; };
