@@ -40,6 +40,7 @@ def lib():
         L.oracle_raycast.argtypes = [vp, f32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.oracle_get_voxel.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         L.oracle_allocate_block.argtypes = [vp, i32, i32, i32]
+        L.oracle_delete_block.argtypes = [vp, i32, i32, i32]
         L.refhash_create.restype = vp
         L.refhash_create.argtypes = [i32, i32]
         L.refhash_destroy.argtypes = [vp]
@@ -139,6 +140,19 @@ class Oracle:
 
     def allocate_block(self, bx, by, bz):
         return self.L.oracle_allocate_block(self.h, bx, by, bz)
+
+    def delete_block(self, bx, by, bz):
+        return self.L.oracle_delete_block(self.h, bx, by, bz)
+
+    def prune_to(self, keys):
+        """Delete every block whose coordinate is not in `keys` (n x 3); returns how many were removed."""
+        keep = set(map(tuple, np.asarray(keys).tolist()))
+        mine = self.export(voxels=False)[0]
+        n = 0
+        for k in mine.tolist():
+            if tuple(k) not in keep:
+                n += self.delete_block(*k)
+        return n
 
 
 def hash_block(x, y, z):

@@ -591,6 +591,15 @@ int oracle_get_voxel(tsdf_oracle* o, int px, int py, int pz, float* tsdf, uint8_
   return 1;
 }
 
+/* Remove a block (used to prune the volume to the reference's block set before comparing RayCast /
+ * Gather outputs with fixtures produced by the racy reference table). */
+int oracle_delete_block(tsdf_oracle* o, int bx, int by, int bz) {
+  int id = map_find(o, pack_key((int16_t)bx, (int16_t)by, (int16_t)bz));
+  if (id < 0) return 0;
+  block_delete(o, id);
+  return 1;
+}
+
 /* Insert a block directly with the acquire-time defaults (hash/pool unit tests). */
 int oracle_allocate_block(tsdf_oracle* o, int bx, int by, int bz) {
   if (map_find(o, pack_key((int16_t)bx, (int16_t)by, (int16_t)bz)) >= 0) return 0;
