@@ -18,9 +18,10 @@ Legs (own arm):
             D2H of both rendered images + hit depth inside the timed region
   cpu       the scalar/OpenMP CPU oracle on a bounded sample of the same workload (rank 0, N=1)
 
-`--impl reference` times the CPU oracle port of the reference path (the reference has no CPU
-implementation and its CUDA needs Eigen/OpenCV/GL) with all host threads.
-Prints ONE JSON line on rank 0.
+`--impl reference` runs the reference's OWN CUDA TSDFGrid (utils/tsdf/*.cu, unmodified, rebuilt for
+sm_100a into oracle/_ref by oracle/build_ref.sh) through its public Integrate / RayCast API on the
+same workload -- the reference has no CPU implementation of this path -- and falls back to the CPU
+oracle port only if that library is absent.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -185,9 +186,15 @@ def cpu_sample(cfg, st, budget_s, max_frames):
 
 
 def run_reference(args, cfg, rank, world):
-    """--impl reference: the oracle port on the host cores, one frame (Integrate + RayCast) per step."""
+    """--impl reference.  Preferred: the reference's OWN CUDA TSDFGrid (utils/tsdf/*.cu, unmodified, rebuilt for
+    sm_100a with its Release flags -> oracle/_ref/libref_tsdf.so) on this box's GPU 0, through its public
+    Integrate / RayCast API, same streams-per-GPU workload as the own arm.  Fallback (library absent): the CPU
+    oracle port on the host cores."""
     if rank != 0:
         return
+    from oracle import ref_cuda
+    if ref_cuda.available(parity=False):
+        return run_reference_cuda(args, cfg)
     from oracle.oracle import Oracle
     n_frames = min(args.lap, args.warmup + args.steps)
     st = generate_streams(cfg, 0, 1, n_frames)[0]
@@ -208,8 +215,58 @@ def run_reference(args, cfg, rank, world):
                                        "oracle/tsdf_oracle.c -O2, OpenMP over visible blocks and image rows, allocation pass scalar"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "the reference has no CPU TSDF path; its CUDA needs Eigen/OpenCV/GL (absent) -- see DESIGN.md"}
+            "note": "oracle/_ref absent: CPU oracle port timed instead of the reference's CUDA rebuild"}
     print(json.dumps(line), flush=True)
+
+
+def run_reference_cuda(args, cfg):
+    from oracle.ref_cuda import RefTSDFGrid
+    B, K, W = args.streams, args.steps, args.warmup
+    n_frames = min(args.lap, W + K)
+    streams = generate_streams(cfg, 0, B, n_frames)
+    grids = [RefTSDFGrid(cfg.voxel_size, cfg.truncation, parity=False) for _ in range(B)]
+    H, Wd = cfg.height, cfg.width
+    npx = H * Wd
+
+    def step(b, i):
+        fi = i % n_frames
+        st, g = streams[b], grids[b]
+        g.integrate(st["rgb"][fi], st["depth"][fi], st["ht"][fi], st["lt"][fi], cfg.max_depth, st["K"], st["q"][fi], st["t"][fi])
+        g.raycast(cfg.max_depth, Wd, H, st["K"], st["q"][fi], st["t"][fi], download=True)
+
+    for i in range(W):
+        for b in range(B):
+            step(b, i)
+    start = threading.Barrier(B + 1)
+
+    def worker(b):
+        start.wait()
+        for i in range(W, W + K):
+            step(b, i)
+
+    ths = [threading.Thread(target=worker, args=(b,)) for b in range(B)]
+    for t in ths:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    act = [g.num_active() for g in grids]
+    v = B * K / dt
+    desc = (f"the reference's own CUDA TSDFGrid (utils/tsdf/*.cu unmodified, -O3 -DNDEBUG, sm_100a) on GPU 0 of this box: {B} streams, "
+            f"one host thread each, TSDFGrid::Integrate(host cv::Mat planes) + TSDFGrid::RayCast + download of both images per frame; "
+            f"{K} timed steps after {W} warm-up; active blocks at end {act}")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(cfg, B, f"{B} independent streams interleaved per GPU, one frame of each per step"), frames_per_step=B),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": B, "kind": "reference", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 15 * npx * B, "d2h_bytes_per_step": 8 * npx * B},
+            "gpu_launches": 0,
+            "note": "the reference has no CPU TSDF path: this arm runs its CUDA kernels (oracle/_ref) on one B200; pageable host buffers as in its API"}
+    print(json.dumps(line), flush=True)
+    for g in grids:
+        g.close()
 
 
 def workload_config(cfg, streams, extra):
