@@ -44,6 +44,7 @@ SYMBOLS = {
     "tsdf_integrate_device": (_i32, _FRAME + [_vp]),
     "tsdf_raycast": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsdf_raycast_device": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsdf_raycast_resident": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "tsdf_gather_valid": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_in_bound": (_i32, [_vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_fetch": (_i32, [_vp, _vp, _i64]),

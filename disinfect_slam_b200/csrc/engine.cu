@@ -393,6 +393,18 @@ int tsdf_raycast(tsdf_handle e, float max_depth, int w, int h, const float K[4],
   return TSDF_OK;
 }
 
+int tsdf_raycast_resident(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                          const void** d_rgba, const void** d_normal, const void** d_hit_depth) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if ((int64_t)w * h > e->cfg.max_image_pixels) return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
+  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, e->rgba, e->normal, e->hit_depth, nullptr);
+  if (rc) return rc;
+  if (d_rgba) *d_rgba = e->rgba;
+  if (d_normal) *d_normal = e->normal;
+  if (d_hit_depth) *d_hit_depth = e->hit_depth;
+  return TSDF_OK;
+}
+
 static int select_blocks(tsdf_engine* e, const float* bbox, int* n_sel) {
   GridBound g{};
   if (bbox) {  // BoundingCube::Scale<short>(1. / voxel_size), voxel_tsdf.cuh:21-26, voxel_tsdf.cu:429

@@ -118,6 +118,14 @@ int tsdf_raycast_device(tsdf_handle h, float max_depth, int width, int height, c
                         const float q_xyzw[4], const float t_xyz[3], void* d_rgba, void* d_normal,
                         void* d_hit_depth, void* d_packed_min_keys);
 
+/* Engine-owned output variant: renders into the engine's own device images (the reference's
+ * img_tsdf_rgba_ / img_tsdf_normal_, voxel_tsdf.cuh:121-122) and returns their device addresses,
+ * valid until the next raycast -- what a GLImage8UC4::LoadCuda-style sink consumes.  Asynchronous
+ * on the engine stream; any output pointer may be NULL. */
+int tsdf_raycast_resident(tsdf_handle h, float max_depth, int width, int height, const float K[4],
+                          const float q_xyzw[4], const float t_xyz[3], const void** d_rgba, const void** d_normal,
+                          const void** d_hit_depth);
+
 /* TSDFGrid::GatherValid()                               utils/tsdf/voxel_tsdf.cu:399-425
  * TSDFGrid::GatherVoxels(BoundingCube<float>)           utils/tsdf/voxel_tsdf.cu:427-454
  * out = array of VoxelSpatialTSDF {float x, y, z, tsdf} (utils/tsdf/voxel_types.cuh:48-57),
