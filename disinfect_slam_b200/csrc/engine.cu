@@ -34,7 +34,7 @@ enum { PH_UPLOAD = 0, PH_ALLOC, PH_SELECT, PH_INTEGRATE, PH_RAYCAST, PH_GATHER, 
 
 struct FrameBuf {
   unsigned char* rgb = nullptr; float *depth = nullptr, *ht = nullptr, *lt = nullptr;
-  TexA* texA = nullptr; TexB* texB = nullptr;
+  Texel* tex = nullptr;
   cudaEvent_t uploaded = nullptr, done = nullptr;
   int* h_ctr = nullptr;  // pinned copy of the device counters after this frame
   bool in_flight = false;
@@ -137,13 +137,13 @@ static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned c
                           const float* ht, const float* lt, FrameBuf& f) {
   cudaMemsetAsync(e->S.ctr + C_PER_CALL, 0, sizeof(int) * (C_COUNT - C_PER_CALL), e->stream);
   phase_begin(e, PH_ALLOC, e->stream);
-  launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.texA, f.texB, e->stream);
+  launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.tex, e->stream);
   phase_end(e, PH_ALLOC, e->stream);
   phase_begin(e, PH_SELECT, e->stream);
   launch_select_visible(e->S, P, e->visible, e->num_sms, e->stream);
   phase_end(e, PH_SELECT, e->stream);
   phase_begin(e, PH_INTEGRATE, e->stream);
-  launch_integrate_carve(e->S, P, e->visible, f.texA, f.texB, e->num_sms, e->stream);
+  launch_integrate_carve(e->S, P, e->visible, f.tex, e->num_sms, e->stream);
   phase_end(e, PH_INTEGRATE, e->stream);
   cudaMemcpyAsync(f.h_ctr, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream);
   cudaEventRecord(f.done, e->stream);
@@ -257,7 +257,7 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
     CUX(cudaMalloc(&f.rgb, 3 * npx)); CUX(cudaMalloc(&f.depth, 4 * npx)); CUX(cudaMalloc(&f.ht, 4 * npx)); CUX(cudaMalloc(&f.lt, 4 * npx));
-    CUX(cudaMalloc(&f.texA, sizeof(TexA) * npx)); CUX(cudaMalloc(&f.texB, sizeof(TexB) * npx));
+    CUX(cudaMalloc(&f.tex, sizeof(Texel) * npx));
     CUX(cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
     CUX(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
     CUX(cudaMallocHost(&f.h_ctr, sizeof(int) * C_COUNT));
@@ -283,7 +283,7 @@ int tsdf_destroy(tsdf_handle e) {
   cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr);
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
-    cudaFree(f.rgb); cudaFree(f.depth); cudaFree(f.ht); cudaFree(f.lt); cudaFree(f.texA); cudaFree(f.texB);
+    cudaFree(f.rgb); cudaFree(f.depth); cudaFree(f.ht); cudaFree(f.lt); cudaFree(f.tex);
     if (f.uploaded) cudaEventDestroy(f.uploaded);
     if (f.done) cudaEventDestroy(f.done);
     if (f.h_ctr) cudaFreeHost(f.h_ctr);

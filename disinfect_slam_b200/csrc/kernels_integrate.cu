@@ -14,9 +14,9 @@ namespace tsdf {
 
 // ------------------------------------------------------------------------------------------
 // frame_allocate_kernel: one thread per pixel.
-//  (1) staging: TexA{depth|0, range}, TexB{log ht - log lt, w_new, rgb} -- everything the
-//      integrate kernel needs per pixel in two aligned gathers, with the per-pixel work
-//      (range norm, depth/max_depth division, logs) done once per pixel instead of once per voxel.
+//  (1) staging: Texel{depth|0, range, log ht - log lt, rgb} -- everything the integrate kernel
+//      needs per pixel in ONE aligned 16-byte gather, with the per-pixel work (range norm, logs)
+//      done once per pixel instead of once per voxel.
 //  (2) DDA over +-truncation along the pixel ray; candidate blocks are de-duplicated across the
 //      warp with match.any before the (L2-resident) table is probed; only absent blocks pay the
 //      8-corner visibility test and the CAS insert.
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) frame_allocate_kernel(DeviceState S, Fram
                                                              const float* __restrict__ depth,
                                                              const float* __restrict__ ht,
                                                              const float* __restrict__ lt,
-                                                             TexA* __restrict__ texA, TexB* __restrict__ texB) {
+                                                             Texel* __restrict__ tex) {
   const int npix = P.w * P.h;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_img = idx < npix;
@@ -43,14 +43,10 @@ __global__ void __launch_bounds__(256) frame_allocate_kernel(DeviceState S, Fram
     pos_cam = kmul(P.Kinv, f3((float)x, (float)y, 1.f));
     range = sqrtf(sqnorm3(pos_cam));
     valid = !(d == 0 || d > P.max_depth);
-    TexA a; a.depth = valid ? d : 0.f; a.range = range;
-    texA[idx] = a;
-    TexB b;
-    b.dlogit = logf(ht[idx]) - logf(lt[idx]);
-    b.w_new = (1 - d / P.max_depth) * 4;  // voxel_tsdf.cu:182
-    b.rgbx = (uint32_t)rgb[3 * idx] | ((uint32_t)rgb[3 * idx + 1] << 8) | ((uint32_t)rgb[3 * idx + 2] << 16);
-    b.pad = 0;
-    texB[idx] = b;
+    const float dlogit = logf(ht[idx]) - logf(lt[idx]);
+    const uint32_t rgbx = (uint32_t)rgb[3 * idx] | ((uint32_t)rgb[3 * idx + 1] << 8) | ((uint32_t)rgb[3 * idx + 2] << 16);
+    *reinterpret_cast<uint4*>(tex + idx) =
+        make_uint4(__float_as_uint(valid ? d : 0.f), __float_as_uint(range), __float_as_uint(dlogit), rgbx);
   }
 
   // ---- ray set-up, utils/tsdf/voxel_tsdf.cu:124-139 ----
@@ -147,149 +143,194 @@ __global__ void __launch_bounds__(256) select_visible_kernel(DeviceState S, Fram
 }
 
 // ------------------------------------------------------------------------------------------
-// integrate_carve_kernel: persistent CTAs of 128 threads; one visible block per iteration,
-// 4 consecutive-x voxels per thread so that every voxel plane access is one 16-byte
-// LDG/STG and a warp covers 512 contiguous bytes.
+// integrate_carve_kernel: persistent warps, ONE WARP PER VISIBLE BLOCK taken from a device-side
+// queue (no block barrier, no shared memory).  The warp walks the block in four 128-voxel slabs;
+// a lane owns 4 consecutive-x voxels of a slab, so every voxel-plane access is one 16-byte LDG/STG
+// and the warp covers 512 contiguous bytes per plane.  A slab's three planes are requested before
+// its projection arithmetic, its 4 pixel gathers are issued together, and the next block's
+// directory entry is fetched one block ahead.
 //   per voxel: voxel_tsdf.cu:157-203 (projection, nearest pixel, SDF, truncation, weighted
 //   running averages, weight clamp); per block: voxel_tsdf.cu:214-229 (min |tsdf| >= .9 -> free).
-// Fusions: blocks acquired this frame are initialised in registers (no init pass, no read);
-// carved blocks are never written back; the carve reduction reuses the just-computed values.
+// Fusions: blocks acquired this frame are initialised in registers (no init pass, no read); the
+// carve reduction reuses the just-computed values; the per-pixel inputs arrive in one 16-byte
+// gather; divisions share one refined reciprocal per divisor (div_by, bit-identical to `/`).
 // ------------------------------------------------------------------------------------------
+#ifndef INTEGRATE_MIN_CTAS
+#define INTEGRATE_MIN_CTAS 4  // 64 registers -> 32 resident warps per SM (measured faster than 80 registers / 24 warps)
+#endif
 __device__ __forceinline__ float4 ld16(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ uint4 ld16u(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st16u(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+// (int)roundf(x) for 0 <= x < 2^23 (and NaN -> 0, like cvt.rzi of roundf(NaN)): what roundf itself does
+__device__ __forceinline__ unsigned round_nonneg(float x) { return (unsigned)__float2int_rz(__fadd_rz(x, 0.5f)); }
 
-__global__ void __launch_bounds__(128) integrate_carve_kernel(DeviceState S, FrameParams P,
+__global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kernel(DeviceState S, FrameParams P,
                                                               const int* __restrict__ visible,
-                                                              const TexA* __restrict__ texA,
-                                                              const TexB* __restrict__ texB,
-                                                              float carve_threshold) {
-  __shared__ float s_min[4];
-  const int t = threadIdx.x;
-  const int lane = t & 31, warp = t >> 5;
+                                                              const Texel* __restrict__ tex, float carve_threshold) {
+  const unsigned lane = threadIdx.x & 31;
   const int n_vis = S.ctr[C_NVIS];
-  const int vx0 = (t & 1) * 4, vy = (t >> 1) & 7, vz = t >> 4;  // voxel t*4 .. t*4+3 of the block
+  const int vx0 = (lane & 1) * 4, vy = (lane >> 1) & 7, vz_lo = lane >> 4;  // voxel (slab * 32 + lane) * 4 .. + 3
+  const bool fast_trunc = div_safe(P.truncation), fast_md = div_safe(P.max_depth);
+  const float r_trunc = rcp_refined(P.truncation), r_md = rcp_refined(P.max_depth);
+  const float qx = P.cam_T_world.qx, qy = P.cam_T_world.qy, qz = P.cam_T_world.qz, qw = P.cam_T_world.qw;
   unsigned n_upd_thread = 0;
   int n_carved_thread = 0;
 
-  for (int b = blockIdx.x; b < n_vis; b += gridDim.x) {
-    const int idx = visible[b];
-    const u64 bk = S.block_key[idx];
+  // device-side queue of visible blocks; the next block's directory entry is fetched one block ahead
+  int b = 0;
+  if (lane == 0) b = atomicAdd(&S.ctr[C_WORK], 1);
+  b = __shfl_sync(0xFFFFFFFFu, b, 0);
+  int idx = 0; u64 bk = 0;
+  if (b < n_vis) { idx = visible[b]; bk = S.block_key[idx]; }
+
+  while (b < n_vis) {
+    int b_next = 0;
+    if (lane == 0) b_next = atomicAdd(&S.ctr[C_WORK], 1);
+    b_next = __shfl_sync(0xFFFFFFFFu, b_next, 0);
+    int idx_next = 0; u64 bk_next = 0;
+    if (b_next < n_vis) { idx_next = visible[b_next]; bk_next = S.block_key[idx_next]; }
+
     const bool is_new = (bk & kFlagNew) != 0;
     int bx, by, bz; unpack_key(bk, bx, by, bz);
-    float* p_tsdf = block_tsdf(S, idx) + t * 4;
-    uint32_t* p_rgbw = block_rgbw(S, idx) + t * 4;
-    float* p_logit = block_logit(S, idx) + t * 4;
+    float* const base_tsdf = block_tsdf(S, idx) + lane * 4;
+    uint32_t* const base_rgbw = block_rgbw(S, idx) + lane * 4;
+    float* const base_logit = block_logit(S, idx) + lane * 4;
 
-    // the TSDF plane is always needed (carve test); issue the load before the projection maths
-    float tsdf[4];
-    if (!is_new) { const float4 v = ld16(p_tsdf); tsdf[0] = v.x; tsdf[1] = v.y; tsdf[2] = v.z; tsdf[3] = v.w; }
-    else { tsdf[0] = tsdf[1] = tsdf[2] = tsdf[3] = -1.f; }  // voxel_mem.cu:49
+    float block_min = 2.f;
+    const int gy = (short)((by << 3) + vy);
+    const float wy = (float)gy * P.voxel_size;
 
-    // ---- projection + decision (voxel_tsdf.cu:157-176) ----
-    const int gy = (short)((by << 3) + vy), gz = (short)((bz << 3) + vz);
-    int pix[4];
-    float tsdf_new[4];
-    unsigned upd = 0;
+#pragma unroll 1
+    for (int slab = 0; slab < 4; ++slab) {
+      // the three planes of this slab: requested now, first needed after the projection + gather below
+      float4 c_tsdf = make_float4(-1.f, -1.f, -1.f, -1.f);  // voxel_mem.cu:48-50: tsdf -1, weight 0 (rgb := 0), p .5
+      uint4 c_rgbw = make_uint4(0u, 0u, 0u, 0u);
+      float4 c_logit = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!is_new) { c_tsdf = ld16(base_tsdf + slab * 128); c_rgbw = ld16u(base_rgbw + slab * 128); c_logit = ld16(base_logit + slab * 128); }
+      // ---- SE3::Apply in Eigen's order (qrot, tsdf_device.cuh), x-independent part hoisted ----
+      const int gz = (short)((bz << 3) + slab * 2 + vz_lo);
+      const float wz = (float)gz * P.voxel_size;
+      const float uvx = qy * wz - qz * wy;          // uv = q.vec x v
+      const float uvx2 = uvx + uvx;                 // uv += uv
+      const float qx_wz = qx * wz, qx_wy = qx * wy;
+      const float qw_uvx2 = qw * uvx2, qz_uvx2 = qz * uvx2, qy_uvx2 = qy * uvx2;
+      // ---- phase 1: project the 4 voxels (voxel_tsdf.cu:157-166) ----
+      float pcz[4];
+      int pix[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gx = (short)((bx << 3) + vx0 + j);
-      const float3 pos_world = f3((float)gx * P.voxel_size, (float)gy * P.voxel_size, (float)gz * P.voxel_size);
-      const float3 pos_cam = apply(P.cam_T_world, pos_world);
-      const float3 pos_img_h = kmul(P.K, pos_cam);
-      const int u = __float2int_rz(roundf(pos_img_h.x / pos_img_h.z));
-      const int v = __float2int_rz(roundf(pos_img_h.y / pos_img_h.z));
-      pix[j] = -1;
-      tsdf_new[j] = 0.f;
-      if (u >= 0 && u < P.w && v >= 0 && v < P.h) {
-        const int img_idx = v * P.w + u;
-        const float2 araw = __ldg(reinterpret_cast<const float2*>(texA + img_idx));
-        TexA a; a.depth = araw.x; a.range = araw.y;
-        if (a.depth != 0.f) {  // depth == 0 || depth > max_depth folded into the staging
-          const float sdf = a.range * (a.depth - pos_img_h.z);
+      for (int j = 0; j < 4; ++j) {
+        const int gx = (short)((bx << 3) + vx0 + j);
+        const float wx = (float)gx * P.voxel_size;
+        const float uvy = qz * wx - qx_wz, uvz = qx_wy - qy * wx;
+        const float uvy2 = uvy + uvy, uvz2 = uvz + uvz;
+        const float cx = qy * uvz2 - qz * uvy2;      // q.vec x uv
+        const float cy = qz_uvx2 - qx * uvz2;
+        const float cz = qx * uvy2 - qy_uvx2;
+        const float pcx = ((wx + qw_uvx2) + cx) + P.cam_T_world.tx;
+        const float pcy = ((wy + qw * uvy2) + cy) + P.cam_T_world.ty;
+        pcz[j] = ((wz + qw * uvz2) + cz) + P.cam_T_world.tz;
+        const float hx = P.K.fx * pcx + P.K.cx * pcz[j], hy = P.K.fy * pcy + P.K.cy * pcz[j];  // kmul
+        float uq, vq;
+        if (div_safe(pcz[j])) { const float r = rcp_refined(pcz[j]); uq = div_by(hx, pcz[j], r); vq = div_by(hy, pcz[j], r); }
+        else { uq = hx / pcz[j]; vq = hy / pcz[j]; }
+        const int u = __float2int_rz(roundf(uq)), v = __float2int_rz(roundf(vq));
+        pix[j] = (u >= 0 && u < P.w && v >= 0 && v < P.h) ? v * P.w + u : -1;
+      }
+      // ---- phase 2: the 4 pixel gathers in flight together (depth 0 <=> nothing to do) ----
+      uint4 px[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        px[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (pix[j] >= 0) px[j] = __ldg(reinterpret_cast<const uint4*>(tex + pix[j]));
+      }
+      // ---- phase 3: update (voxel_tsdf.cu:167-203) ----
+      float tsdf[4] = {c_tsdf.x, c_tsdf.y, c_tsdf.z, c_tsdf.w};
+      uint32_t rgbw[4] = {c_rgbw.x, c_rgbw.y, c_rgbw.z, c_rgbw.w};
+      float logit[4] = {c_logit.x, c_logit.y, c_logit.z, c_logit.w};
+      unsigned upd = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float depth = __uint_as_float(px[j].x);
+        if (depth != 0.f) {  // depth == 0 || depth > max_depth folded into the staging
+          const float sdf = __uint_as_float(px[j].y) * (depth - pcz[j]);
           if (sdf > -P.truncation) {
-            tsdf_new[j] = fminf(1, sdf / P.truncation);
-            pix[j] = img_idx;
             upd |= 1u << j;
+            const float tsdf_new = fminf(1, fast_trunc ? div_by(sdf, P.truncation, r_trunc) : sdf / P.truncation);
+            const float weight_new = (1 - (fast_md ? div_by(depth, P.max_depth, r_md) : depth / P.max_depth)) * 4;  // :182
+            const float weight_old = (float)(rgbw[j] >> 24);
+            const float weight_combined = weight_old + weight_new;
+            const float r_old = (float)(rgbw[j] & 0xFF), g_old = (float)((rgbw[j] >> 8) & 0xFF), b_old = (float)((rgbw[j] >> 16) & 0xFF);
+            const float r_new = (float)(px[j].w & 0xFF), g_new = (float)((px[j].w >> 8) & 0xFF), b_new = (float)((px[j].w >> 16) & 0xFF);
+            // voxel_tsdf.cu:186-202 (semantic fusion in logit space)
+            const float num_r = r_old * weight_old + r_new * weight_new, num_g = g_old * weight_old + g_new * weight_new,
+                        num_b = b_old * weight_old + b_new * weight_new;
+            const float num_t = tsdf[j] * weight_old + tsdf_new * weight_new;
+            const float num_l = logit[j] * weight_old + __uint_as_float(px[j].z) * weight_new;
+            if (div_safe(weight_combined)) {
+              const float rw = rcp_refined(weight_combined);
+              const unsigned r = round_nonneg(div_by(num_r, weight_combined, rw)), g = round_nonneg(div_by(num_g, weight_combined, rw)),
+                             bb = round_nonneg(div_by(num_b, weight_combined, rw));
+              tsdf[j] = div_by(num_t, weight_combined, rw);
+              logit[j] = div_by(num_l, weight_combined, rw);
+              rgbw[j] = r | (g << 8) | (bb << 16) | (min(round_nonneg(weight_combined), 40u) << 24);
+            } else {  // e.g. depth == max_depth on a fresh voxel: 0 / 0 like the reference
+              const unsigned r = (unsigned)__float2int_rz(roundf(num_r / weight_combined)), g = (unsigned)__float2int_rz(roundf(num_g / weight_combined)),
+                             bb = (unsigned)__float2int_rz(roundf(num_b / weight_combined));
+              tsdf[j] = num_t / weight_combined;
+              logit[j] = num_l / weight_combined;
+              const unsigned w = (unsigned)__float2int_rz(fminf(roundf(weight_combined), 40));
+              rgbw[j] = min(r, 255u) | (min(g, 255u) << 8) | (min(bb, 255u) << 16) | (w << 24);
+            }
           }
         }
       }
-    }
-
-    // ---- colour / weight / semantic planes only when this thread updates something ----
-    uint32_t rgbw[4] = {0u, 0u, 0u, 0u};          // weight 0 (voxel_mem.cu:48); rgb defined as 0
-    float logit[4] = {0.f, 0.f, 0.f, 0.f};        // probability .5 (voxel_mem.cu:50)
-    if (upd && !is_new) {
-      const uint4 c = ld16u(p_rgbw); rgbw[0] = c.x; rgbw[1] = c.y; rgbw[2] = c.z; rgbw[3] = c.w;
-      const float4 l = ld16(p_logit); logit[0] = l.x; logit[1] = l.y; logit[2] = l.z; logit[3] = l.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (upd & (1u << j)) {
-        const float4 braw = __ldg(reinterpret_cast<const float4*>(texB + pix[j]));
-        TexB tb; tb.dlogit = braw.x; tb.w_new = braw.y; tb.rgbx = __float_as_uint(braw.z);
-        const float weight_new = tb.w_new;
-        const float weight_old = (float)(rgbw[j] >> 24);
-        const float weight_combined = weight_old + weight_new;
-        // voxel_tsdf.cu:186-194
-        const float r_old = (float)(rgbw[j] & 0xFF), g_old = (float)((rgbw[j] >> 8) & 0xFF),
-                    b_old = (float)((rgbw[j] >> 16) & 0xFF);
-        const float r_new = (float)(tb.rgbx & 0xFF), g_new = (float)((tb.rgbx >> 8) & 0xFF),
-                    b_new = (float)((tb.rgbx >> 16) & 0xFF);
-        const unsigned r = (unsigned)__float2int_rz(roundf((r_old * weight_old + r_new * weight_new) / weight_combined));
-        const unsigned g = (unsigned)__float2int_rz(roundf((g_old * weight_old + g_new * weight_new) / weight_combined));
-        const unsigned bb = (unsigned)__float2int_rz(roundf((b_old * weight_old + b_new * weight_new) / weight_combined));
-        tsdf[j] = (tsdf[j] * weight_old + tsdf_new[j] * weight_new) / weight_combined;
-        const unsigned w = (unsigned)__float2int_rz(fminf(roundf(weight_combined), 40));
-        rgbw[j] = (min(r, 255u)) | (min(g, 255u) << 8) | (min(bb, 255u) << 16) | (w << 24);
-        // voxel_tsdf.cu:196-202 in logit space: logit' = (w_old*logit + w_new*(log ht - log lt)) / w
-        logit[j] = (logit[j] * weight_old + tb.dlogit * weight_new) / weight_combined;
+      n_upd_thread += __popc(upd);
+      block_min = fminf(block_min, fminf(fminf(fabsf(tsdf[0]), fabsf(tsdf[1])), fminf(fabsf(tsdf[2]), fabsf(tsdf[3]))));
+      if (upd || is_new) {  // a block that turns out to be carved is released anyway: writing it is harmless
+        st16(base_tsdf + slab * 128, make_float4(tsdf[0], tsdf[1], tsdf[2], tsdf[3]));
+        st16u(base_rgbw + slab * 128, make_uint4(rgbw[0], rgbw[1], rgbw[2], rgbw[3]));
+        st16(base_logit + slab * 128, make_float4(logit[0], logit[1], logit[2], logit[3]));
       }
     }
-    n_upd_thread += __popc(upd);
 
     // ---- space carving (voxel_tsdf.cu:214-229): min |tsdf| over the 512 voxels ----
-    float m = fminf(fminf(fabsf(tsdf[0]), fabsf(tsdf[1])), fminf(fabsf(tsdf[2]), fabsf(tsdf[3])));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if (lane == 0) s_min[warp] = m;
-    __syncthreads();
-    const float block_min = fminf(fminf(s_min[0], s_min[1]), fminf(s_min[2], s_min[3]));
-    __syncthreads();  // s_min is reused by the next iteration
-
-    if (block_min >= carve_threshold) {
-      if (t == 0) { table_erase(S, bk & kKeyMask); ++n_carved_thread; }
-    } else {
-      if (upd || is_new) {
-        st16(p_tsdf, make_float4(tsdf[0], tsdf[1], tsdf[2], tsdf[3]));
-        st16u(p_rgbw, make_uint4(rgbw[0], rgbw[1], rgbw[2], rgbw[3]));
-        st16(p_logit, make_float4(logit[0], logit[1], logit[2], logit[3]));
-      }
-      if (is_new && t == 0) S.block_key[idx] = bk & kKeyMask;
+    for (int o = 16; o > 0; o >>= 1) block_min = fminf(block_min, __shfl_xor_sync(0xFFFFFFFFu, block_min, o));
+    if (lane == 0) {
+      if (block_min >= carve_threshold) { table_erase(S, bk & kKeyMask); ++n_carved_thread; }
+      else if (is_new) S.block_key[idx] = bk & kKeyMask;
     }
+    b = b_next; idx = idx_next; bk = bk_next;
   }
 
   // ---- counters: one atomic per warp ----
   n_upd_thread = __reduce_add_sync(0xFFFFFFFFu, n_upd_thread);
-  if (lane == 0 && n_upd_thread) atomicAdd(reinterpret_cast<u64*>(&S.ctr[C_NUPD_LO]), (u64)n_upd_thread);
-  if (t == 0 && n_carved_thread) atomicAdd(&S.ctr[C_NCARVED], n_carved_thread);
+  if (lane == 0) {
+    if (n_upd_thread) atomicAdd(reinterpret_cast<u64*>(&S.ctr[C_NUPD_LO]), (u64)n_upd_thread);
+    if (n_carved_thread) atomicAdd(&S.ctr[C_NCARVED], n_carved_thread);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const unsigned char* rgb, const float* depth,
-                           const float* ht, const float* lt, TexA* texA, TexB* texB, cudaStream_t st) {
+                           const float* ht, const float* lt, Texel* tex, cudaStream_t st) {
   const int npix = P.w * P.h;
-  frame_allocate_kernel<<<(npix + 255) / 256, 256, 0, st>>>(S, P, rgb, depth, ht, lt, texA, texB);
+  frame_allocate_kernel<<<(npix + 255) / 256, 256, 0, st>>>(S, P, rgb, depth, ht, lt, tex);
 }
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int num_sms, cudaStream_t st) {
   select_visible_kernel<<<num_sms * 4, 256, 0, st>>>(S, P, visible);
 }
-void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, const TexA* texA,
-                            const TexB* texB, int num_sms, cudaStream_t st) {
-  integrate_carve_kernel<<<num_sms * 8, 128, 0, st>>>(S, P, visible, texA, texB, .9f);
+void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, const Texel* tex,
+                            int num_sms, cudaStream_t st) {
+  static int ctas_per_sm = 0;  // persistent warps: exactly the resident CTAs, work comes from the device-side queue
+  if (ctas_per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, integrate_carve_kernel, 256, 0) != cudaSuccess || ctas_per_sm < 1)
+      ctas_per_sm = 2;
+  }
+  integrate_carve_kernel<<<num_sms * ctas_per_sm, 256, 0, st>>>(S, P, visible, tex, .9f);
 }
 
 }  // namespace tsdf

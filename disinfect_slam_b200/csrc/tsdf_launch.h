@@ -8,10 +8,10 @@ namespace tsdf {
 
 // kernels_integrate.cu
 void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const unsigned char* rgb, const float* depth,
-                           const float* ht, const float* lt, TexA* texA, TexB* texB, cudaStream_t st);
+                           const float* ht, const float* lt, Texel* tex, cudaStream_t st);
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int num_sms, cudaStream_t st);
-void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, const TexA* texA,
-                            const TexB* texB, int num_sms, cudaStream_t st);
+void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, const Texel* tex,
+                            int num_sms, cudaStream_t st);
 
 // kernels_raycast.cu
 void launch_build_skip_map(const DeviceState& S, const SkipMap& M, int num_sms, cudaStream_t st);
