@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
   uchar4 out_rgba = make_uchar4(0, 0, 0, 0), out_normal = make_uchar4(0, 0, 0, 0);
   float out_depth = CUDART_INF_F;
 
+  bool hit = false;
   for (;;) {
     if (skip > 0) {  // the next `skip` samples read +1: advance the position exactly as the reference does
       const int k = min(skip, max_step - i);
@@ -194,46 +195,49 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
     if (i >= max_step) break;
     const float tsdf_curr = march_sample(S, G, cache, pos_grid, inv_smax, skip);
     // ray hit front surface (voxel_tsdf.cu:260)
-    if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) {
-      float3 pos1 = f3(pos_grid.x - ray_step_grid.x, pos_grid.y - ray_step_grid.y, pos_grid.z - ray_step_grid.z);
-      float3 pos2 = pos_grid;
-      float3 mid = f3((pos1.x + pos2.x) / 2.f, (pos1.y + pos2.y) / 2.f, (pos1.z + pos2.z) / 2.f);
-      // binary search refinement; `> .1` compares in double in the reference, i.e. >= 0.1f for floats
-      for (;;) {
-        const float3 dd = f3(pos1.x - pos2.x, pos1.y - pos2.y, pos1.z - pos2.z);
-        if (!(dot3(dd, dd) >= 0.1f)) break;
-        const float tm = fetch_tsdf_f(S, G, cache, mid);
-        if (tm < 0) pos2 = mid; else pos1 = mid;
-        mid = f3((pos1.x + pos2.x) / 2.f, (pos1.y + pos2.y) / 2.f, (pos1.z + pos2.z) / 2.f);
-      }
-      const int fx = round_to_voxel(mid.x), fy = round_to_voxel(mid.y), fz = round_to_voxel(mid.z);
-      cache_lookup(S, G, cache, fx, fy, fz);
-      uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
-      float prob = 0.f;
-      if (cache.idx >= 0) {
-        const int k = voxel_index(fx, fy, fz);
-        rgbw = __ldg(block_rgbw(S, cache.idx) + k);
-        prob = logit_to_prob(__ldg(block_logit(S, cache.idx) + k));
-      }
-      // central differences on nearest voxels (voxel_tsdf.cu:280-291); short arithmetic wraps like the reference
-      const float gxp = fetch_tsdf(S, G, cache, (short)(fx + 1), fy, fz), gxn = fetch_tsdf(S, G, cache, (short)(fx - 1), fy, fz);
-      const float gyp = fetch_tsdf(S, G, cache, fx, (short)(fy + 1), fz), gyn = fetch_tsdf(S, G, cache, fx, (short)(fy - 1), fz);
-      const float gzp = fetch_tsdf(S, G, cache, fx, fy, (short)(fz + 1)), gzn = fetch_tsdf(S, G, cache, fx, fy, (short)(fz - 1));
-      const float3 nrm = f3(gxp - gxn, gyp - gyn, gzp - gzn);
-      const float3 neg_dir = f3(-ray_dir_world.x, -ray_dir_world.y, -ray_dir_world.z);
-      const float diffusivity = fmaxf(dot3(nrm, neg_dir) / sqrtf(sqnorm3(nrm)), 0);
-      const float alpha = fmaxf(prob - 0.5f, 0) * 2.f;  // == fmaxf(p - .5, 0) / .5 exactly
-      const float r = (float)(rgbw & 0xFF), g = (float)((rgbw >> 8) & 0xFF), b = (float)((rgbw >> 16) & 0xFF);
-      out_rgba = make_uchar4(f2u8(alpha * 255 + (1 - alpha) * r), f2u8((1 - alpha) * g), f2u8((1 - alpha) * b), 255);
-      out_normal = make_uchar4(f2u8(alpha * 255 + (1 - alpha) * diffusivity * 255), f2u8((1 - alpha) * diffusivity * 255),
-                               f2u8((1 - alpha) * diffusivity * 255), 255);
-      const float3 pc = apply(P.cam_T_world, f3(mid.x * P.voxel_size, mid.y * P.voxel_size, mid.z * P.voxel_size));
-      out_depth = pc.z;
-      break;
-    }
+    if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) { hit = true; break; }
     tsdf_prev = tsdf_curr;
     pos_grid = add3(pos_grid, ray_step_grid);
     ++i;
+  }
+
+  // The refinement runs after the march loop so that the lanes of a warp execute it together (once per
+  // warp) instead of once per distinct hit iteration.
+  if (hit) {
+    float3 pos1 = f3(pos_grid.x - ray_step_grid.x, pos_grid.y - ray_step_grid.y, pos_grid.z - ray_step_grid.z);
+    float3 pos2 = pos_grid;
+    float3 mid = f3((pos1.x + pos2.x) / 2.f, (pos1.y + pos2.y) / 2.f, (pos1.z + pos2.z) / 2.f);
+    // binary search refinement; `> .1` compares in double in the reference, i.e. >= 0.1f for floats
+    for (;;) {
+      const float3 dd = f3(pos1.x - pos2.x, pos1.y - pos2.y, pos1.z - pos2.z);
+      if (!(dot3(dd, dd) >= 0.1f)) break;
+      const float tm = fetch_tsdf_f(S, G, cache, mid);
+      if (tm < 0) pos2 = mid; else pos1 = mid;
+      mid = f3((pos1.x + pos2.x) / 2.f, (pos1.y + pos2.y) / 2.f, (pos1.z + pos2.z) / 2.f);
+    }
+    const int fx = round_to_voxel(mid.x), fy = round_to_voxel(mid.y), fz = round_to_voxel(mid.z);
+    cache_lookup(S, G, cache, fx, fy, fz);
+    uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
+    float prob = 0.f;
+    if (cache.idx >= 0) {
+      const int k = voxel_index(fx, fy, fz);
+      rgbw = __ldg(block_rgbw(S, cache.idx) + k);
+      prob = logit_to_prob(__ldg(block_logit(S, cache.idx) + k));
+    }
+    // central differences on nearest voxels (voxel_tsdf.cu:280-291); short arithmetic wraps like the reference
+    const float gxp = fetch_tsdf(S, G, cache, (short)(fx + 1), fy, fz), gxn = fetch_tsdf(S, G, cache, (short)(fx - 1), fy, fz);
+    const float gyp = fetch_tsdf(S, G, cache, fx, (short)(fy + 1), fz), gyn = fetch_tsdf(S, G, cache, fx, (short)(fy - 1), fz);
+    const float gzp = fetch_tsdf(S, G, cache, fx, fy, (short)(fz + 1)), gzn = fetch_tsdf(S, G, cache, fx, fy, (short)(fz - 1));
+    const float3 nrm = f3(gxp - gxn, gyp - gyn, gzp - gzn);
+    const float3 neg_dir = f3(-ray_dir_world.x, -ray_dir_world.y, -ray_dir_world.z);
+    const float diffusivity = fmaxf(dot3(nrm, neg_dir) / sqrtf(sqnorm3(nrm)), 0);
+    const float alpha = fmaxf(prob - 0.5f, 0) * 2.f;  // == fmaxf(p - .5, 0) / .5 exactly
+    const float r = (float)(rgbw & 0xFF), g = (float)((rgbw >> 8) & 0xFF), b = (float)((rgbw >> 16) & 0xFF);
+    out_rgba = make_uchar4(f2u8(alpha * 255 + (1 - alpha) * r), f2u8((1 - alpha) * g), f2u8((1 - alpha) * b), 255);
+    out_normal = make_uchar4(f2u8(alpha * 255 + (1 - alpha) * diffusivity * 255), f2u8((1 - alpha) * diffusivity * 255),
+                             f2u8((1 - alpha) * diffusivity * 255), 255);
+    const float3 pc = apply(P.cam_T_world, f3(mid.x * P.voxel_size, mid.y * P.voxel_size, mid.z * P.voxel_size));
+    out_depth = pc.z;
   }
 
   if (img_rgba) img_rgba[idx] = out_rgba;
