@@ -53,6 +53,7 @@ SYMBOLS = {
     "tsdf_get_counters": (_i32, [_vp, C.POINTER(Counters)]),
     "tsdf_synchronize": (_i32, [_vp]),
     "tsdf_stream": (_vp, [_vp]),
+    "tsdf_block_owner": (_i32, [C.c_int16, C.c_int16, C.c_int16, _i32, _i32]),
     "tsdf_hash": (C.c_uint32, [C.c_int16, C.c_int16, C.c_int16]),
     "tsdf_allocate_blocks": (_i32, [_vp, _vp, _i32]),
     "tsdf_delete_blocks": (_i32, [_vp, _vp, _i32]),

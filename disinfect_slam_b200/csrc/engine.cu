@@ -243,7 +243,7 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   CUX(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   DeviceState& S = e->S;
   S.table_mask = (unsigned)cfg.table_slots - 1; S.pool_blocks = cfg.pool_blocks;
-  S.shard_rank = cfg.shard_rank; S.shard_count = cfg.shard_count;
+  S.shard_rank = cfg.shard_rank; S.shard_count = cfg.shard_count; S.shard_shift = cfg.flags & TSDF_FLAG_SHARD_SHIFT_MASK;
   CUX(cudaMalloc(&S.table, sizeof(Slot) * (size_t)cfg.table_slots));
   CUX(cudaMalloc(&S.block_key, sizeof(u64) * (size_t)cfg.pool_blocks));
   CUX(cudaMalloc(&S.voxels, (size_t)kBlockBytes * (size_t)cfg.pool_blocks));
@@ -486,6 +486,11 @@ int tsdf_get_counters(tsdf_handle e, tsdf_counters* out) {
   int rc = drain(e);
   *out = e->last;
   return rc;
+}
+
+int tsdf_block_owner(int16_t bx, int16_t by, int16_t bz, int shard_count, int shard_shift) {
+  if (shard_count < 1 || shard_shift < 0 || shard_shift > 15) return -1;
+  return (int)owner_of(pack_key(bx, by, bz), shard_count, shard_shift);
 }
 
 uint32_t tsdf_hash(int16_t bx, int16_t by, int16_t bz) { return hash_block(bx, by, bz) & ((1u << 21) - 1); }

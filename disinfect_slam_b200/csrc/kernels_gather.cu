@@ -100,7 +100,7 @@ __global__ void allocate_list_kernel(DeviceState S, const short* __restrict__ ke
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u64 key = pack_key(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]);
-  if (S.shard_count > 1 && owner_of(key, S.shard_count) != (unsigned)S.shard_rank) return;
+  if (S.shard_count > 1 && owner_of(key, S.shard_count, S.shard_shift) != (unsigned)S.shard_rank) return;
   if (table_insert(S, key) == 1) atomicAdd(&S.ctr[C_NNEW], 1);
 }
 // blocks inserted outside Integrate are materialised immediately (the integrate kernel normally

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) frame_allocate_kernel(DeviceState S, Fram
     // warp-cooperative de-duplication: one lane per distinct block coordinate probes the table
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
     const bool leader = (key != kEmpty) && ((unsigned)(__ffs(peers) - 1) == lane);
-    if (leader && (S.shard_count <= 1 || owner_of(key, S.shard_count) == (unsigned)S.shard_rank)) {
+    if (leader && (S.shard_count <= 1 || owner_of(key, S.shard_count, S.shard_shift) == (unsigned)S.shard_rank)) {
       ++n_cand;
       int bx, by, bz; unpack_key(key, bx, by, bz);
       // Allocate() is a no-op for present blocks (voxel_hash.cu:62-77), so probe before the

@@ -43,6 +43,13 @@ def hash_block(bx, by, bz):
     return int(_lib.lib().tsdf_hash(bx, by, bz))
 
 
+def block_owner(keys, shard_count, shard_shift=0):
+    """Owner rank of each block coordinate (n x 3) under the engine's sharding rule, through the C ABI."""
+    L = _lib.lib()
+    return np.array([L.tsdf_block_owner(int(k[0]), int(k[1]), int(k[2]), int(shard_count), int(shard_shift))
+                     for k in np.asarray(keys).reshape(-1, 3)], np.int32)
+
+
 class PinnedArray:
     """numpy view of pinned host memory from tsdf_host_alloc (DMA-able Integrate inputs)."""
 
@@ -65,7 +72,7 @@ class PinnedArray:
 
 class TSDFGrid:
     def __init__(self, voxel_size, truncation, pool_blocks=None, table_slots=None, max_image_pixels=None, device=None,
-                 shard_rank=0, shard_count=1):
+                 shard_rank=0, shard_count=1, shard_shift=0):
         self.L = _lib.lib()
         self.voxel_size, self.truncation = float(voxel_size), float(truncation)
         cfg = Config()
@@ -81,6 +88,7 @@ class TSDFGrid:
         if device is not None:
             cfg.device = int(device)
         cfg.shard_rank, cfg.shard_count = int(shard_rank), int(shard_count)
+        cfg.flags = int(shard_shift) & 0xF
         self.cfg = cfg
         self.h = C.c_void_p()
         check(self.L.tsdf_create(voxel_size, truncation, C.byref(cfg), C.byref(self.h)))

@@ -46,6 +46,8 @@ typedef struct tsdf_engine* tsdf_handle;
 /* Runtime replacements for the reference's compile-time #defines
  * (NUM_BLOCK utils/tsdf/voxel_mem.cuh:11-12, NUM_ENTRY utils/tsdf/voxel_hash.cuh:13-25,
  *  MAX_IMG_SIZE utils/tsdf/voxel_tsdf.cu:10-12). */
+#define TSDF_FLAG_SHARD_SHIFT_MASK 0xF
+
 typedef struct tsdf_config {
   int32_t struct_size;      /* = sizeof(tsdf_config) */
   int32_t device;           /* CUDA ordinal; -1 = current device */
@@ -54,7 +56,7 @@ typedef struct tsdf_config {
   int32_t max_image_pixels; /* largest W*H accepted (default 1920 * 1080) */
   int32_t shard_rank;       /* multi-GPU block ownership: this engine keeps only blocks with */
   int32_t shard_count;      /*   owner(block) == shard_rank of shard_count (default 0 of 1) */
-  int32_t flags;            /* reserved, 0 */
+  int32_t flags;            /* bits 0..3: shard granularity shift s -- (1 << s)^3 neighbouring blocks share an owner */
 } tsdf_config;
 
 /* Counters of the last tsdf_integrate* call (what the reference only logs through
@@ -151,6 +153,10 @@ void* tsdf_stream(tsdf_handle h);
 /* Hash(block_pos) & BUCKET_MASK                         utils/tsdf/voxel_hash.cu:31-35
  * (21-bit mask of the reference; the engine uses the same mix, masked to its own table size). */
 uint32_t tsdf_hash(int16_t bx, int16_t by, int16_t bz);
+
+/* Rank that owns block (bx, by, bz) when the volume is sharded over shard_count engines with
+ * granularity shift shard_shift (pure host function; the same mix the kernels use). */
+int tsdf_block_owner(int16_t bx, int16_t by, int16_t bz, int shard_count, int shard_shift);
 
 /* Parity / unit-test access (what utils/tests/voxel_hash_test.cu:36-55 does with its own
  * Allocate / Retrieve / Assignment kernels, and voxel_mem_test.cu with Aquire/Release).
