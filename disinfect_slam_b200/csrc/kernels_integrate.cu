@@ -27,11 +27,13 @@ __global__ void __launch_bounds__(256) frame_allocate_kernel(DeviceState S, Fram
                                                              const float* __restrict__ ht,
                                                              const float* __restrict__ lt,
                                                              Texel* __restrict__ tex) {
-  const int npix = P.w * P.h;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_img = idx < npix;
-  const int y = in_img ? idx / P.w : 0;
-  const int x = in_img ? idx - y * P.w : 0;
+  // CTA = 32 x 8 pixels, warp = 8 x 4 pixels: the pixels of a warp fall into one or two blocks, so the
+  // match.any de-duplication below leaves about one table probe per warp and DDA step
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+  const int y = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+  const bool in_img = x < P.w && y < P.h;
+  const int idx = y * P.w + x;
 
   float d = 0.f;
   float3 pos_cam = f3(0.f, 0.f, 1.f);
@@ -49,31 +51,38 @@ __global__ void __launch_bounds__(256) frame_allocate_kernel(DeviceState S, Fram
         make_uint4(__float_as_uint(valid ? d : 0.f), __float_as_uint(range), __float_as_uint(dlogit), rgbx);
   }
 
-  // ---- ray set-up, utils/tsdf/voxel_tsdf.cu:124-139 ----
+  // ---- ray set-up, utils/tsdf/voxel_tsdf.cu:124-139 (divisions share one reciprocal per divisor, see div_by) ----
   int nsteps = 0;
   float3 pos_grid = f3(0.f, 0.f, 0.f), ray_step_grid = f3(0.f, 0.f, 0.f);
   if (valid) {
     const float3 pos_world = apply(P.world_T_cam, f3(pos_cam.x * d, pos_cam.y * d, pos_cam.z * d));
-    const float3 ray_dir_cam = f3(pos_cam.x / range, pos_cam.y / range, pos_cam.z / range);
+    float3 ray_dir_cam;
+    if (div_safe(range)) { const float r = rcp_refined(range); ray_dir_cam = f3(div_by(pos_cam.x, range, r), div_by(pos_cam.y, range, r), div_by(pos_cam.z, range, r)); }
+    else ray_dir_cam = f3(pos_cam.x / range, pos_cam.y / range, pos_cam.z / range);
     const float3 ray_dir_world = qrot(P.world_T_cam, ray_dir_cam);
     const float3 ray_start_world = f3(pos_world.x - ray_dir_world.x * P.truncation,
                                       pos_world.y - ray_dir_world.y * P.truncation,
                                       pos_world.z - ray_dir_world.z * P.truncation);
-    const float3 ray_dir_grid = f3(ray_dir_world.x / P.voxel_size, ray_dir_world.y / P.voxel_size,
-                                   ray_dir_world.z / P.voxel_size);
-    pos_grid = f3(ray_start_world.x / P.voxel_size, ray_start_world.y / P.voxel_size,
-                  ray_start_world.z / P.voxel_size);
+    float3 ray_dir_grid;
+    if (div_safe(P.voxel_size)) {
+      const float r = rcp_refined(P.voxel_size);
+      ray_dir_grid = f3(div_by(ray_dir_world.x, P.voxel_size, r), div_by(ray_dir_world.y, P.voxel_size, r), div_by(ray_dir_world.z, P.voxel_size, r));
+      pos_grid = f3(div_by(ray_start_world.x, P.voxel_size, r), div_by(ray_start_world.y, P.voxel_size, r), div_by(ray_start_world.z, P.voxel_size, r));
+    } else {
+      ray_dir_grid = f3(ray_dir_world.x / P.voxel_size, ray_dir_world.y / P.voxel_size, ray_dir_world.z / P.voxel_size);
+      pos_grid = f3(ray_start_world.x / P.voxel_size, ray_start_world.y / P.voxel_size, ray_start_world.z / P.voxel_size);
+    }
     const float two_t = 2 * P.truncation;
     const float3 ray_grid = f3(two_t * ray_dir_grid.x, two_t * ray_dir_grid.y, two_t * ray_dir_grid.z);
     const int step_grid =
         __float2int_rz(ceilf(fmaxf(fmaxf(fabsf(ray_grid.x), fabsf(ray_grid.y)), fabsf(ray_grid.z)) / kBlockLen));
     const float denom = fmaxf((float)step_grid, 1);
-    ray_step_grid = f3(ray_grid.x / denom, ray_grid.y / denom, ray_grid.z / denom);
+    if (div_safe(denom)) { const float r = rcp_refined(denom); ray_step_grid = f3(div_by(ray_grid.x, denom, r), div_by(ray_grid.y, denom, r), div_by(ray_grid.z, denom, r)); }
+    else ray_step_grid = f3(ray_grid.x / denom, ray_grid.y / denom, ray_grid.z / denom);
     nsteps = step_grid + 1;  // for (i = 0; i <= step_grid; ++i)
   }
 
   const int max_steps = __reduce_max_sync(0xFFFFFFFFu, nsteps);
-  const unsigned lane = threadIdx.x & 31;
   u64 prev_key = kEmpty;
   int n_cand = 0, n_new = 0;
   for (int i = 0; i < max_steps; ++i) {
@@ -317,8 +326,7 @@ __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kerne
 // ------------------------------------------------------------------------------------------
 void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const unsigned char* rgb, const float* depth,
                            const float* ht, const float* lt, Texel* tex, cudaStream_t st) {
-  const int npix = P.w * P.h;
-  frame_allocate_kernel<<<(npix + 255) / 256, 256, 0, st>>>(S, P, rgb, depth, ht, lt, tex);
+  frame_allocate_kernel<<<dim3((P.w + 31) / 32, (P.h + 7) / 8), 256, 0, st>>>(S, P, rgb, depth, ht, lt, tex);
 }
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int num_sms, cudaStream_t st) {
   select_visible_kernel<<<num_sms * 4, 256, 0, st>>>(S, P, visible);

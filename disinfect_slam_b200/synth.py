@@ -51,7 +51,7 @@ def config(name):
     c1 = SceneConfig("config1_tum_640x480_1cm", 640, 480, TUM_K, 0.01, 0.06, 4.0, 100)
     k2 = tuple(2.0 * v for v in L515_HALF_K)
     c2 = SceneConfig("config2_l515_1280x720_5mm", 1280, 720, k2, 0.005, 0.03, 4.0, 100, depth_factor=4000.0,
-                     pool_blocks=1 << 20, table_slots=1 << 23)
+                     pool_blocks=1 << 18, table_slots=1 << 20)  # the reference's NUM_BLOCK; a lap peaks near 70 k blocks
     c2h = SceneConfig("config2_l515_640x360_5mm", 640, 360, L515_HALF_K, 0.005, 0.03, 4.0, 100, depth_factor=4000.0,
                       pool_blocks=1 << 20, table_slots=1 << 23)
     c3 = SceneConfig("config3_room_1280x720_2cm", 1280, 720, k2, 0.02, 0.12, 4.0, 200, room_half=(8.0, 3.0, 8.0),

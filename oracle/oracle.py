@@ -41,6 +41,7 @@ def lib():
         L.oracle_get_voxel.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         L.oracle_allocate_block.argtypes = [vp, i32, i32, i32]
         L.oracle_delete_block.argtypes = [vp, i32, i32, i32]
+        L.oracle_set_voxel.argtypes = [vp, i32, i32, i32, vp, vp, vp]
         L.refhash_create.restype = vp
         L.refhash_create.argtypes = [i32, i32]
         L.refhash_destroy.argtypes = [vp]
@@ -140,6 +141,14 @@ class Oracle:
 
     def allocate_block(self, bx, by, bz):
         return self.L.oracle_allocate_block(self.h, bx, by, bz)
+
+    def set_voxels(self, points, tsdf=None, rgbw=None, prob=None):
+        pts = np.asarray(points, np.int32).reshape(-1, 3)
+        for i, (x, y, z) in enumerate(pts.tolist()):
+            t = None if tsdf is None else C.byref(C.c_float(float(tsdf[i])))
+            p = None if prob is None else C.byref(C.c_float(float(prob[i])))
+            c = None if rgbw is None else _p(np.ascontiguousarray(rgbw[i], np.uint8))
+            assert self.L.oracle_set_voxel(self.h, x, y, z, t, c, p) == 1
 
     def delete_block(self, bx, by, bz):
         return self.L.oracle_delete_block(self.h, bx, by, bz)

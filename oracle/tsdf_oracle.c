@@ -591,6 +591,18 @@ int oracle_get_voxel(tsdf_oracle* o, int px, int py, int pz, float* tsdf, uint8_
   return 1;
 }
 
+/* Overwrite one voxel of an existing block (testing aid: hand-built volumes); NULL leaves a field. */
+int oracle_set_voxel(tsdf_oracle* o, int px, int py, int pz, const float* tsdf, const uint8_t* rgbw4, const float* prob) {
+  int id = map_find(o, pack_key((int16_t)(px >> 3), (int16_t)(py >> 3), (int16_t)(pz >> 3)));
+  if (id < 0) return 0;
+  oblock* b = o->blocks[id];
+  const int k = vox_index((int16_t)px, (int16_t)py, (int16_t)pz);
+  if (tsdf) b->tsdf[k] = *tsdf;
+  if (rgbw4) memcpy(b->rgbw + k * 4, rgbw4, 4);
+  if (prob) b->prob[k] = *prob;
+  return 1;
+}
+
 /* Remove a block (used to prune the volume to the reference's block set before comparing RayCast /
  * Gather outputs with fixtures produced by the racy reference table). */
 int oracle_delete_block(tsdf_oracle* o, int bx, int by, int bz) {
