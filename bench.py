@@ -484,7 +484,13 @@ def main():
     kern_total = sum(ph_ms.get(k, 0.0) for k in ("allocate", "select", "integrate", "raycast"))
     kernels = {k: {"ms_per_launch": ph_ms[k] / max(ph_n[k], 1), "share_of_step_kernel_time": ph_ms[k] / kern_total if kern_total else 0.0}
                for k in ("allocate", "select", "integrate", "raycast")}
-    ws = (n_vis * 6144 + 39 * npx * tot["frames"]) / max(K, 1)
+    ws = (n_vis * 6144 + 31 * npx * tot["frames"]) / max(K, 1)  # voxel blocks + 15 B/px planes + 16 B/px staging
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("integrate_carve_kernel", {}).get("dram_bytes_per_launch")
+    except Exception:
+        tj = {}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -496,12 +502,16 @@ def main():
         "raycast_mrays_per_s": frames * npx / (ms * 1e-3) / 1e6,
         "integrate_frame_hbm_gbs": frame_bytes / ((ph_ms.get("allocate", 0) + ph_ms.get("select", 0) + integ_ms) * 1e-3) / 1e9 if integ_ms else None,
         "roofline": {"kernel": "integrate_carve_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": tj.get("source"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": integ_bytes / launches, "us_per_launch": 1e3 * integ_ms / launches,
                      "launches_timed": launches},
         "kernels": kernels,
+        "raycast": {"us_per_view": 1e3 * ph_ms.get("raycast", 0.0) / max(ph_n.get("raycast", 0), 1), "rays_per_view": npx,
+                    "mrays_per_s_kernel_only": npx * ph_n.get("raycast", 0) / (ph_ms.get("raycast", 1e-9) * 1e-3) / 1e6,
+                    "note": "skip-map build + march; issue/latency bound (ncu: DRAM < 6 % of peak), not an HBM-roofline kernel"},
         "e2e": e2e,
-        "gpu_launches": 4 * B * K,
+        # per frame: frame_allocate, select_visible, integrate_carve + skip_prepare, skip_fill, skip_mark, 3 x skip_pass, raycast
+        "gpu_launches": 10 * B * K,
         "clocks": sampler.summary(windows[:1]),
         "counters_per_frame": {k: tot[k] / max(tot["frames"], 1) for k in ("n_new", "n_visible", "n_updated", "n_carved", "n_active_post")},
     }

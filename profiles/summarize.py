@@ -55,7 +55,19 @@ def full(tag):
         for c in cols:
             out.append(f"{h[c]:62s} {r[c][:60]:>24s} {units[c]}")
     open(os.path.join(ROOT, "profiles", f"{tag}_full.txt"), "w").write("\n".join(out) + "\n")
-    print("\n".join(out[:60]))
+    # per-kernel DRAM traffic per launch (mean over the captured launches) -> profiles/traffic.json, read by bench.py
+    import json
+    ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows:
+        name = r[ki].split("(")[0]
+        acc.setdefault(name, []).append(float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]])
+    tj = {"source": f"profiles/{tag}_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"}
+    for name, v in acc.items():
+        tj[name] = {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v)}
+    json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    print("\n".join(out[:20]))
 
 
 if __name__ == "__main__":
