@@ -484,6 +484,8 @@ def main():
     kern_total = sum(ph_ms.get(k, 0.0) for k in ("allocate", "select", "integrate", "raycast"))
     kernels = {k: {"ms_per_launch": ph_ms[k] / max(ph_n[k], 1), "share_of_step_kernel_time": ph_ms[k] / kern_total if kern_total else 0.0}
                for k in ("allocate", "select", "integrate", "raycast")}
+    kernels["skipmap"] = {"ms_per_launch": ph_ms.get("skipmap", 0.0) / max(ph_n.get("skipmap", 0), 1),
+                          "note": "6 launches on a side stream, overlapped with select + integrate; not part of the serial sum"}
     ws = (n_vis * 6144 + 31 * npx * tot["frames"]) / max(K, 1)  # voxel blocks + 15 B/px planes + 16 B/px staging
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed ncu capture
     try:
