@@ -399,7 +399,7 @@ int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const floa
     cudaStreamWaitEvent(e->stream, e->ev_map, 0);
     e->map_pending = false;
   }
-  e->eager_map = true;
+  e->eager_map = false;  // eager build beside integrate measured no gain: the persistent integrate CTAs hold the whole register file
   launch_raycast(e->S, P, e->truncation / 2, e->skip, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
                  (unsigned long long*)d_packed, e->stream);  // step = truncation / 2, voxel_tsdf.cu:497
   phase_end(e, PH_RAYCAST, e->stream);
