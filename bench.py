@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded single-stream leg at N > 1")
     ap.add_argument("--scale", type=float, default=1.0, help="image scale (debug only; 1.0 = the named config)")
     return ap.parse_args()
 
@@ -194,7 +195,9 @@ def run_reference(args, cfg, rank, world):
         return
     from oracle import ref_cuda
     if ref_cuda.available(parity=False):
-        return run_reference_cuda(args, cfg)
+        import torch
+        if torch.cuda.is_available():
+            return run_reference_cuda(args, cfg)
     from oracle.oracle import Oracle
     n_frames = min(args.lap, args.warmup + args.steps)
     st = generate_streams(cfg, 0, 1, n_frames)[0]
@@ -216,7 +219,7 @@ def run_reference(args, cfg, rank, world):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "oracle/_ref absent: CPU oracle port timed instead of the reference's CUDA rebuild"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_reference_cuda(args, cfg):
@@ -264,7 +267,7 @@ def run_reference_cuda(args, cfg):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 15 * npx * B, "d2h_bytes_per_step": 8 * npx * B},
             "gpu_launches": 0,
             "note": "the reference has no CPU TSDF path: this arm runs its CUDA kernels (oracle/_ref) on one B200; pageable host buffers as in its API"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     for g in grids:
         g.close()
 
@@ -276,9 +279,85 @@ def workload_config(cfg, streams, extra):
 
 
 # --------------------------------------------------------------------------------------------------
+# sharded single-stream leg (N > 1): block-coordinate ownership, NCCL frame broadcast, min-composited RayCast
+# --------------------------------------------------------------------------------------------------
+def sharded_leg(args, cfg, st, d0, rank, world, local_rank, dev, n_frames, W, K):
+    import torch
+    import torch.distributed as dist
+    from disinfect_slam_b200 import sharded, tsdf_grid
+    H, Wd = cfg.height, cfg.width
+    n = H * Wd
+    # camera of every frame of rank 0's stream 0, shared once up front
+    cams = torch.zeros((n_frames, 7), dtype=torch.float32, device=dev)
+    if rank == 0:
+        cams.copy_(torch.from_numpy(np.concatenate([np.stack(st["q"]), np.stack(st["t"])], 1).astype(np.float32)))
+    Kt = torch.tensor(np.asarray(st["K"], np.float32) if rank == 0 else np.zeros(4, np.float32), device=dev)
+    dist.broadcast(cams, src=0)
+    dist.broadcast(Kt, src=0)
+    cams, Kv = cams.cpu().numpy(), Kt.cpu().numpy()
+    cam = tsdf_grid.CameraParams(Kv, H, Wd)
+    # packed [depth | ht | lt | rgb] frames, resident on the root; receive buffers elsewhere
+    if rank == 0:
+        packed = [torch.cat([d0["depth"][i].reshape(-1).view(torch.uint8), d0["ht"][i].reshape(-1).view(torch.uint8),
+                             d0["lt"][i].reshape(-1).view(torch.uint8), d0["rgb"][i].reshape(-1)]) for i in range(n_frames)]
+    else:
+        packed = [torch.empty(15 * n, dtype=torch.uint8, device=dev) for _ in range(3)]
+    g = sharded.ShardedTSDFGrid(cfg.voxel_size, cfg.truncation, device=local_rank, shard_shift=2, pool_blocks=cfg.pool_blocks,
+                                table_slots=cfg.table_slots, max_image_pixels=n)
+
+    def step(i):
+        fi = i % n_frames
+        buf = packed[fi] if rank == 0 else packed[i % 3]
+        q, t = cams[fi, :4], cams[fi, 4:]
+        g.IntegrateBroadcast(buf, Wd, H, cfg.max_depth, Kv, q, t)
+        return g.RayCastKeys(cfg.max_depth, cam, (q, t))
+
+    for i in range(W):
+        step(i)
+    g.synchronize()
+    g.backend.grid.set_profiling(False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        keys = step(i)
+    g.synchronize()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    tot = g.backend.grid.totals()
+    cnt = torch.tensor([tot["n_updated"], tot["n_visible"], g.backend.num_active()], device=dev, dtype=torch.int64)
+    allc = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    hits = int((keys.view(-1, 2)[:, 0] < sharded.MISS_KEY).sum().item())
+    g.close()
+    dt = float(dt.item())
+    upd = sum(int(c[0]) for c in allc)
+    return {"frames_per_s": K / dt, "ms_per_frame": 1e3 * dt / K, "voxel_updates_per_s": upd / dt, "raycast_mrays_per_s": K * n / dt / 1e6,
+            "active_blocks_per_rank": [int(c[2]) for c in allc], "visible_blocks_per_rank_per_frame": [int(c[1]) / K for c in allc],
+            "last_view_hit_fraction": hits / n, "shard_shift": 2,
+            "collectives_per_frame": f"1 NCCL broadcast of {15 * n} B + 1 NCCL all-reduce(MIN) of {16 * n} B",
+            "timing": "host clock around K frames bracketed by synchronize + barrier, max over ranks (engine and NCCL streams are chained by events)"}
+
+
+# --------------------------------------------------------------------------------------------------
 # own arm
 # --------------------------------------------------------------------------------------------------
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (e.g. NCCL's version banner)
+    was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -458,6 +537,10 @@ def main():
         for g in engs:
             g.close()
         del engs
+    # ---------------- leg 4 (N > 1): ONE stream whose volume is sharded over all ranks ----------------
+    shard = None
+    if world > 1 and not args.no_sharded:
+        shard = sharded_leg(args, cfg, streams[0], dres[0], rank, world, local_rank, dev, n_frames, W, K)
     sampler.stop()
 
     if rank != 0:
@@ -517,6 +600,8 @@ def main():
         "clocks": sampler.summary(windows[:1]),
         "counters_per_frame": {k: tot[k] / max(tot["frames"], 1) for k in ("n_new", "n_visible", "n_updated", "n_carved", "n_active_post")},
     }
+    if shard is not None:
+        line["sharded_single_stream"] = shard
     if not args.no_cpu_baseline and world == 1:
         v, n, dt = cpu_sample(cfg, streams[0], args.cpu_seconds, n_frames)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": oracle_threads(), "kind": "port",
@@ -524,7 +609,7 @@ def main():
                                           "OpenMP over visible blocks and image rows, allocation pass scalar"}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -52,6 +52,7 @@ class EngineBackend:
         self.grid = tsdf_grid.TSDFGrid(voxel_size, truncation, device=device, shard_rank=rank, shard_count=world,
                                        shard_shift=shard_shift, **kw)
         self._keys = None
+        self.ext = torch.cuda.ExternalStream(self.grid.stream(), device=self.device)  # the engine's own stream
 
     def integrate(self, planes, w, h, max_depth, K, q, t):
         ev = torch.cuda.Event()  # the broadcast ran on torch's stream: the engine stream waits for it on the device
@@ -64,7 +65,9 @@ class EngineBackend:
             self._keys = torch.empty(2 * w * h, dtype=torch.int64, device=self.device)
         cam = tsdf_grid.CameraParams(K, h, w)
         self.grid.RayCastDevice(max_depth, cam, (q, t), d_packed=self._keys.data_ptr())
-        self.grid.synchronize()
+        ev = torch.cuda.Event()  # the collective (torch's stream) waits for the engine stream on the device, not on the host
+        ev.record(self.ext)
+        torch.cuda.current_stream(self.device).wait_event(ev)
         return self._keys
 
     def gather(self, bbox):
