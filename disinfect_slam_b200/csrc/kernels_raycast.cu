@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
   for (;;) {
     if (skip > 0) {  // the next `skip` samples read +1: advance the position exactly as the reference does
       const int k = min(skip, max_step - i);
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < k; ++j) pos_grid = add3(pos_grid, ray_step_grid);
       i += k;
     }
@@ -217,17 +217,34 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
     }
     const int fx = round_to_voxel(mid.x), fy = round_to_voxel(mid.y), fz = round_to_voxel(mid.z);
     cache_lookup(S, G, cache, fx, fy, fz);
-    uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
-    float prob = 0.f;
-    if (cache.idx >= 0) {
-      const int k = voxel_index(fx, fy, fz);
-      rgbw = __ldg(block_rgbw(S, cache.idx) + k);
-      prob = logit_to_prob(__ldg(block_logit(S, cache.idx) + k));
+    const int cidx = cache.idx;
+    // Block index of each of the 6 neighbours first (only a neighbour across a block face needs a table lookup,
+    // at most one per axis), then all 8 voxel loads of the hit -- colour, logit and the 6 gradient samples -- are
+    // independent and in flight together (voxel_tsdf.cu:277-291; short arithmetic wraps like the reference).
+    const int nx[6] = {(short)(fx + 1), (short)(fx - 1), fx, fx, fx, fx};
+    const int ny[6] = {fy, fy, (short)(fy + 1), (short)(fy - 1), fy, fy};
+    const int nz[6] = {fz, fz, fz, fz, (short)(fz + 1), (short)(fz - 1)};
+    int nidx[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) {
+      nidx[n] = cidx;
+      if (((nx[n] ^ fx) | (ny[n] ^ fy) | (nz[n] ^ fz)) >> 3) {  // different block coordinate
+        const int bx = nx[n] >> 3, by = ny[n] >> 3, bz = nz[n] >> 3;
+        nidx[n] = cell_distance(G, bx, by, bz) == 0 ? table_find(S, pack_key(bx, by, bz)) : -1;
+      }
     }
-    // central differences on nearest voxels (voxel_tsdf.cu:280-291); short arithmetic wraps like the reference
-    const float gxp = fetch_tsdf(S, G, cache, (short)(fx + 1), fy, fz), gxn = fetch_tsdf(S, G, cache, (short)(fx - 1), fy, fz);
-    const float gyp = fetch_tsdf(S, G, cache, fx, (short)(fy + 1), fz), gyn = fetch_tsdf(S, G, cache, fx, (short)(fy - 1), fz);
-    const float gzp = fetch_tsdf(S, G, cache, fx, fy, (short)(fz + 1)), gzn = fetch_tsdf(S, G, cache, fx, fy, (short)(fz - 1));
+    uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
+    float lgt = 0.f;
+    if (cidx >= 0) {
+      const int k = voxel_index(fx, fy, fz);
+      rgbw = __ldg(block_rgbw(S, cidx) + k);
+      lgt = __ldg(block_logit(S, cidx) + k);
+    }
+    float gv[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) gv[n] = nidx[n] >= 0 ? __ldg(block_tsdf(S, nidx[n]) + voxel_index(nx[n], ny[n], nz[n])) : 1.f;
+    const float prob = cidx >= 0 ? logit_to_prob(lgt) : 0.f;
+    const float gxp = gv[0], gxn = gv[1], gyp = gv[2], gyn = gv[3], gzp = gv[4], gzn = gv[5];
     const float3 nrm = f3(gxp - gxn, gyp - gyn, gzp - gzn);
     const float3 neg_dir = f3(-ray_dir_world.x, -ray_dir_world.y, -ray_dir_world.z);
     const float diffusivity = fmaxf(dot3(nrm, neg_dir) / sqrtf(sqnorm3(nrm)), 0);
