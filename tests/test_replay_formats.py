@@ -1,0 +1,71 @@
+"""CPU tests of the reference's on-disk formats (disinfect_slam_b200/replay.py): log round trip, pixel
+conversion rules, rotation-matrix -> quaternion conversion, TSDF dump records; plus a GPU test that a log
+replayed through the engine equals the oracle fed with the same decoded frames."""
+import numpy as np
+import pytest
+
+from disinfect_slam_b200 import replay, synth
+from oracle.oracle import Oracle
+
+
+def test_quaternion_from_rotation_all_branches():
+    rng = np.random.RandomState(5)
+    qs = [np.array([0, 0, 0, 1.0]), np.array([1.0, 0, 0, 0.001]), np.array([0, 1.0, 0, 0.001]), np.array([0, 0.001, 1.0, 0])]
+    qs += [rng.randn(4) for _ in range(50)]
+    for q in qs:
+        q = q / np.linalg.norm(q)
+        R = replay.rotation_from_quat(q)
+        q2 = replay.quat_from_rotation(R).astype(np.float64)
+        assert abs(np.linalg.norm(q2) - 1) < 1e-5
+        assert min(np.abs(q2 - q).max(), np.abs(q2 + q).max()) < 2e-6, (q, q2)
+
+
+def test_log_round_trip(tmp_path):
+    cfg = synth.config("tiny")
+    sc = synth.Scene(cfg)
+    frames = [sc.frame(i) for i in range(3)]
+    replay.write_log(str(tmp_path), frames, cfg.depth_factor)
+    got = list(replay.read_log(str(tmp_path), cfg.depth_factor))
+    assert [g["id"] for g in got] == [0, 1, 2]
+    for f, g in zip(frames, got):
+        assert np.array_equal(g["rgb"], f["rgb"])
+        # synthetic depth is already quantised to 1 / depth_factor: the 16-bit round trip is the convertTo rule
+        d16 = np.rint(f["depth"].astype(np.float64) * cfg.depth_factor)
+        assert np.array_equal(g["depth"], (d16 * (1.0 / cfg.depth_factor)).astype(np.float32))
+        assert np.abs(g["depth"] - f["depth"]).max() < 1e-6
+        assert np.abs(g["ht"] - f["ht"]).max() <= 0.5 / 65535 + 1e-7 and g["ht"].dtype == np.float32
+        assert min(np.abs(g["q"] - f["q"]).max(), np.abs(g["q"] + f["q"]).max()) < 1e-6 and np.abs(g["t"] - f["t"]).max() < 1e-6
+    # a log without probability images: ht = 0, lt = 1 (examples/tsdf/offline.cc:80-82)
+    for f in frames:
+        f["ht"] = f["lt"] = None
+    replay.write_log(str(tmp_path / "nop"), frames, cfg.depth_factor)
+    g = next(replay.read_log(str(tmp_path / "nop"), cfg.depth_factor))
+    assert (g["ht"] == 0).all() and (g["lt"] == 1).all()
+
+
+def test_tsdf_dump_records(tmp_path):
+    cfg = synth.config("tiny")
+    f = synth.Scene(cfg).frame(0)
+    o = Oracle(cfg.voxel_size, cfg.truncation)
+    o.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"])
+    rec = o.gather()
+    p = tmp_path / "data.bin"
+    replay.save_tsdf_dump(str(p), rec)
+    assert p.stat().st_size == 16 * len(rec)
+    assert np.array_equal(replay.load_tsdf_dump(str(p)).view(np.uint32), rec.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_replayed_log_matches_oracle(tmp_path, tsdf_lib):
+    from disinfect_slam_b200 import tsdf_grid
+    from oracle import compare
+    cfg = synth.config("tiny")
+    sc = synth.Scene(cfg)
+    replay.write_log(str(tmp_path), [sc.frame(i) for i in range(4)], cfg.depth_factor)
+    g = tsdf_grid.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots)
+    assert replay.replay(g, str(tmp_path), cfg.depth_factor, cfg.K, cfg.max_depth) == 4
+    o = Oracle(cfg.voxel_size, cfg.truncation)
+    for f in replay.read_log(str(tmp_path), cfg.depth_factor):
+        o.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, np.array(cfg.K, np.float32), f["q"], f["t"])
+    assert compare.compare_volumes(g.export(), o.export(), "replayed log")["tsdf_bit_exact"]
+    g.close()
