@@ -90,14 +90,14 @@ void launch_build_skip_map(const DeviceState& S, const SkipMap& M, int num_sms, 
 // ray march
 // ------------------------------------------------------------------------------------------
 struct Grid { int ox, oy, oz, nx, ny, nz, shift; const unsigned char* dist; };
-struct BlockCache { u64 key; int idx; };
+struct BlockCache { int bx, by, bz, idx; };  // bx = INT_MIN: nothing cached
 
 // Chebyshev distance (cells) from block (bx,by,bz) to the nearest cell holding an active block;
 // 0 = this cell holds one (the block itself may still be absent when shift > 0)
 __device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int bz) {
   const int cx = (bx - G.ox) >> G.shift, cy = (by - G.oy) >> G.shift, cz = (bz - G.oz) >> G.shift;
   if ((unsigned)cx < (unsigned)G.nx && (unsigned)cy < (unsigned)G.ny && (unsigned)cz < (unsigned)G.nz)
-    return __ldg(G.dist + ((size_t)cz * G.ny + cy) * G.nx + cx);
+    return __ldg(G.dist + ((cz * G.ny + cy) * G.nx + cx));  // at most 2^22 cells
   // outside the AABB: the gap to the box (in cells) is a lower bound of the distance
   const int gx = cx < 0 ? -cx : (cx >= G.nx ? cx - G.nx + 1 : 0);
   const int gy = cy < 0 ? -cy : (cy >= G.ny ? cy - G.ny + 1 : 0);
@@ -107,8 +107,10 @@ __device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int 
 
 __device__ __forceinline__ void cache_lookup(const DeviceState& S, const Grid& G, BlockCache& c, int px, int py, int pz) {
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
-  const u64 key = pack_key(bx, by, bz);
-  if (key != c.key) { c.key = key; c.idx = cell_distance(G, bx, by, bz) == 0 ? table_find(S, key) : -1; }
+  if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
+    c.bx = bx; c.by = by; c.bz = bz;
+    c.idx = cell_distance(G, bx, by, bz) == 0 ? table_find(S, pack_key(bx, by, bz)) : -1;
+  }
 }
 // Retrieve<VoxelTSDF>: absent -> VoxelTSDF() == +1 (voxel_types.cu:8)
 __device__ __forceinline__ float fetch_tsdf(const DeviceState& S, const Grid& G, BlockCache& c, int px, int py, int pz) {
@@ -128,13 +130,12 @@ __device__ __forceinline__ float march_sample(const DeviceState& S, const Grid& 
                                               float inv_smax, int& skip) {
   const int px = round_to_voxel(p.x), py = round_to_voxel(p.y), pz = round_to_voxel(p.z);
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
-  const u64 key = pack_key(bx, by, bz);
   skip = 0;
-  if (key != c.key) {
-    c.key = key;
+  if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
+    c.bx = bx; c.by = by; c.bz = bz;
     const int d = cell_distance(G, bx, by, bz);
     if (d == 0) {
-      c.idx = table_find(S, key);
+      c.idx = table_find(S, pack_key(bx, by, bz));
     } else {
       c.idx = -1;
       if (d >= 2) skip = __float2int_rd((float)(((d - 1) << (3 + G.shift)) - 2) * inv_smax);
@@ -165,23 +166,35 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
   const float3 pos_cam = kmul(P.Kinv, f3((float)x, (float)y, 1.f));
   const float sq = sqnorm3(pos_cam);
   float3 ray_dir_cam = pos_cam;
-  if (sq > 0.f) { const float n = sqrtf(sq); ray_dir_cam = f3(pos_cam.x / n, pos_cam.y / n, pos_cam.z / n); }
+  if (sq > 0.f) {  // normalized(): v / sqrt(squaredNorm)
+    const float n = sqrtf(sq);
+    if (div_safe(n)) { const float r = rcp_refined(n); ray_dir_cam = f3(div_by(pos_cam.x, n, r), div_by(pos_cam.y, n, r), div_by(pos_cam.z, n, r)); }
+    else ray_dir_cam = f3(pos_cam.x / n, pos_cam.y / n, pos_cam.z / n);
+  }
   const float3 ray_dir_world = qrot(P.world_T_cam, ray_dir_cam);
-  const float3 ray_step_grid = f3(ray_dir_world.x * step_size / P.voxel_size, ray_dir_world.y * step_size / P.voxel_size,
-                                  ray_dir_world.z * step_size / P.voxel_size);
+  float3 ray_step_grid, pos_grid;
+  if (div_safe(P.voxel_size)) {  // the six divisions by voxel_size share one reciprocal (div_by: bit-identical to `/`)
+    const float r = rcp_refined(P.voxel_size);
+    ray_step_grid = f3(div_by(ray_dir_world.x * step_size, P.voxel_size, r), div_by(ray_dir_world.y * step_size, P.voxel_size, r),
+                       div_by(ray_dir_world.z * step_size, P.voxel_size, r));
+    pos_grid = f3(div_by(P.world_T_cam.tx, P.voxel_size, r), div_by(P.world_T_cam.ty, P.voxel_size, r), div_by(P.world_T_cam.tz, P.voxel_size, r));
+  } else {
+    ray_step_grid = f3(ray_dir_world.x * step_size / P.voxel_size, ray_dir_world.y * step_size / P.voxel_size,
+                       ray_dir_world.z * step_size / P.voxel_size);
+    pos_grid = f3(P.world_T_cam.tx / P.voxel_size, P.world_T_cam.ty / P.voxel_size, P.world_T_cam.tz / P.voxel_size);
+  }
   const int max_step = __float2int_rz(ceilf(P.max_depth / step_size));
-  float3 pos_grid = f3(P.world_T_cam.tx / P.voxel_size, P.world_T_cam.ty / P.voxel_size, P.world_T_cam.tz / P.voxel_size);
   // conservative 1 / (largest per-step voxel displacement); only used to size skips
   const float smax = fmaxf(fmaxf(fabsf(ray_step_grid.x), fabsf(ray_step_grid.y)), fabsf(ray_step_grid.z));
   const float inv_smax = 1.f / (smax * 1.001f + 1e-6f);
 
-  BlockCache cache; cache.key = kEmpty; cache.idx = -1;
+  BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.idx = -1;
   int skip;
   float tsdf_prev = march_sample(S, G, cache, pos_grid, inv_smax, skip);
   pos_grid = add3(pos_grid, ray_step_grid);
   int i = 1;
 
-  uchar4 out_rgba = make_uchar4(0, 0, 0, 0), out_normal = make_uchar4(0, 0, 0, 0);
+  uint32_t out_rgba = 0u, out_normal = 0u;  // r | g << 8 | b << 16 | a << 24; a miss is (0, 0, 0, 0) like the reference
   float out_depth = CUDART_INF_F;
 
   bool hit = false;
@@ -250,21 +263,22 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
     const float diffusivity = fmaxf(dot3(nrm, neg_dir) / sqrtf(sqnorm3(nrm)), 0);
     const float alpha = fmaxf(prob - 0.5f, 0) * 2.f;  // == fmaxf(p - .5, 0) / .5 exactly
     const float r = (float)(rgbw & 0xFF), g = (float)((rgbw >> 8) & 0xFF), b = (float)((rgbw >> 16) & 0xFF);
-    out_rgba = make_uchar4(f2u8(alpha * 255 + (1 - alpha) * r), f2u8((1 - alpha) * g), f2u8((1 - alpha) * b), 255);
-    out_normal = make_uchar4(f2u8(alpha * 255 + (1 - alpha) * diffusivity * 255), f2u8((1 - alpha) * diffusivity * 255),
-                             f2u8((1 - alpha) * diffusivity * 255), 255);
+    out_rgba = (uint32_t)f2u8(alpha * 255 + (1 - alpha) * r) | ((uint32_t)f2u8((1 - alpha) * g) << 8) |
+               ((uint32_t)f2u8((1 - alpha) * b) << 16) | 0xFF000000u;
+    const uint32_t shade = f2u8((1 - alpha) * diffusivity * 255);
+    out_normal = (uint32_t)f2u8(alpha * 255 + (1 - alpha) * diffusivity * 255) | (shade << 8) | (shade << 16) | 0xFF000000u;
     const float3 pc = apply(P.cam_T_world, f3(mid.x * P.voxel_size, mid.y * P.voxel_size, mid.z * P.voxel_size));
     out_depth = pc.z;
   }
 
-  if (img_rgba) img_rgba[idx] = out_rgba;
-  if (img_normal) img_normal[idx] = out_normal;
+  if (img_rgba) reinterpret_cast<uint32_t*>(img_rgba)[idx] = out_rgba;
+  if (img_normal) reinterpret_cast<uint32_t*>(img_normal)[idx] = out_normal;
   if (img_depth) img_depth[idx] = out_depth;
   if (packed) {
     // positive floats order like unsigned ints; a miss (+inf) loses against every hit
     const u64 dbits = (u64)__float_as_uint(fmaxf(out_depth, 0.f)) << 32;
-    packed[2 * idx + 0] = dbits | (u64)(*reinterpret_cast<const uint32_t*>(&out_rgba));
-    packed[2 * idx + 1] = dbits | (u64)(*reinterpret_cast<const uint32_t*>(&out_normal));
+    packed[2 * idx + 0] = dbits | (u64)out_rgba;
+    packed[2 * idx + 1] = dbits | (u64)out_normal;
   }
 }
 
