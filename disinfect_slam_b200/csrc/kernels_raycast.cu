@@ -25,24 +25,28 @@ namespace tsdf {
 // ------------------------------------------------------------------------------------------
 // skip-map construction (all sizes live on the device: no host round trip)
 // ------------------------------------------------------------------------------------------
-__global__ void skip_prepare_kernel(DeviceState S, SkipMap M) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// header from the AABB counters + fill with the cap.  Every thread derives the same header (a handful of integer
+// operations) so that no separate one-thread launch is needed; thread 0 publishes it for the later kernels.
+__global__ void __launch_bounds__(256) skip_fill_kernel(DeviceState S, SkipMap M) {
   const int x0 = S.ctr[C_MIN_X], y0 = S.ctr[C_MIN_Y], z0 = S.ctr[C_MIN_Z];
   const int x1 = S.ctr[C_MAX_X], y1 = S.ctr[C_MAX_Y], z1 = S.ctr[C_MAX_Z];
-  int* h = M.hdr;
-  if (x1 < x0) { h[0] = h[1] = h[2] = 0; h[3] = h[4] = h[5] = 0; h[6] = 0; h[7] = 0; return; }
-  int shift = 0;
-  long long nx, ny, nz;
-  for (;; ++shift) {
-    nx = ((x1 - x0) >> shift) + 1; ny = ((y1 - y0) >> shift) + 1; nz = ((z1 - z0) >> shift) + 1;
-    if (nx * ny * nz <= (long long)kSkipMaxCells) break;
+  int shift = 0, n = 0;
+  long long nx = 0, ny = 0, nz = 0;
+  if (x1 >= x0) {
+    for (;; ++shift) {
+      nx = ((x1 - x0) >> shift) + 1; ny = ((y1 - y0) >> shift) + 1; nz = ((z1 - z0) >> shift) + 1;
+      if (nx * ny * nz <= (long long)kSkipMaxCells) break;
+    }
+    n = (int)(nx * ny * nz);
   }
-  h[0] = x0; h[1] = y0; h[2] = z0; h[3] = (int)nx; h[4] = (int)ny; h[5] = (int)nz; h[6] = shift; h[7] = (int)(nx * ny * nz);
-}
-
-__global__ void __launch_bounds__(256) skip_fill_kernel(SkipMap M) {
-  const int n = M.hdr[7];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) M.dist[i] = kSkipCap;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int* h = M.hdr;
+    h[0] = n ? x0 : 0; h[1] = n ? y0 : 0; h[2] = n ? z0 : 0; h[3] = (int)nx; h[4] = (int)ny; h[5] = (int)nz; h[6] = shift; h[7] = n;
+  }
+  // 16 bytes per store; the buffer is kSkipMaxCells long, so rounding n up to a multiple of 16 stays inside
+  const uint4 cap16 = make_uint4(0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 15) / 16; i += gridDim.x * blockDim.x)
+    reinterpret_cast<uint4*>(M.dist)[i] = cap16;
 }
 
 __global__ void __launch_bounds__(256) skip_mark_kernel(DeviceState S, SkipMap M) {
@@ -57,32 +61,36 @@ __global__ void __launch_bounds__(256) skip_mark_kernel(DeviceState S, SkipMap M
   }
 }
 
-// one separable pass of the capped Chebyshev distance transform along `axis`:
-//   out(c) = min_k max(in(c +- k e_axis), k)
+// one separable pass of the capped Chebyshev distance transform along AXIS:
+//   out(c) = min_k max(in(c +- k e_axis), k),  k < cap
+// All 2 * (cap - 1) neighbour reads of a cell are independent (no early exit), so they are in flight together.
+template <int AXIS>
 __global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigned char* __restrict__ in,
-                                                        unsigned char* __restrict__ out, int axis) {
+                                                        unsigned char* __restrict__ out) {
   const int nx = M.hdr[3], ny = M.hdr[4], nz = M.hdr[5], n = M.hdr[7];
-  const int len = axis == 0 ? nx : axis == 1 ? ny : nz;
-  const int stride = axis == 0 ? 1 : axis == 1 ? nx : nx * ny;
+  const int len = AXIS == 0 ? nx : AXIS == 1 ? ny : nz;
+  const int stride = AXIS == 0 ? 1 : AXIS == 1 ? nx : nx * ny;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int cx = i % nx, cy = (i / nx) % ny, cz = i / (nx * ny);
-    const int c = axis == 0 ? cx : axis == 1 ? cy : cz;
+    const int c = AXIS == 0 ? i % nx : AXIS == 1 ? (i / nx) % ny : i / (nx * ny);
     int best = in[i];
-    for (int k = 1; k < best; ++k) {
-      if (c - k >= 0) best = min(best, max((int)in[i - k * stride], k));
-      if (c + k < len) best = min(best, max((int)in[i + k * stride], k));
+    if (best > 1) {
+#pragma unroll
+      for (int k = 1; k < kSkipCap; ++k) {
+        const int lo = c - k >= 0 ? (int)in[i - k * stride] : kSkipCap;
+        const int hi = c + k < len ? (int)in[i + k * stride] : kSkipCap;
+        best = min(best, max(min(lo, hi), k));
+      }
     }
     out[i] = (unsigned char)best;
   }
 }
 
 void launch_build_skip_map(const DeviceState& S, const SkipMap& M, int num_sms, cudaStream_t st) {
-  skip_prepare_kernel<<<1, 32, 0, st>>>(S, M);
-  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(M);
+  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(S, M);
   skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(S, M);
-  skip_pass_kernel<<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, 0);
-  skip_pass_kernel<<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist, 1);
-  skip_pass_kernel<<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, 2);
+  skip_pass_kernel<0><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch);
+  skip_pass_kernel<1><<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist);
+  skip_pass_kernel<2><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch);
   // result is in M.scratch; the raycast kernel is launched with the two pointers swapped
 }
 
