@@ -567,8 +567,6 @@ def main():
     kern_total = sum(ph_ms.get(k, 0.0) for k in ("allocate", "select", "integrate", "raycast"))
     kernels = {k: {"ms_per_launch": ph_ms[k] / max(ph_n[k], 1), "share_of_step_kernel_time": ph_ms[k] / kern_total if kern_total else 0.0}
                for k in ("allocate", "select", "integrate", "raycast")}
-    kernels["skipmap"] = {"ms_per_launch": ph_ms.get("skipmap", 0.0) / max(ph_n.get("skipmap", 0), 1),
-                          "note": "6 launches on a side stream, overlapped with select + integrate; not part of the serial sum"}
     ws = (n_vis * 6144 + 31 * npx * tot["frames"]) / max(K, 1)  # voxel blocks + 15 B/px planes + 16 B/px staging
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed ncu capture
     try:
@@ -595,8 +593,8 @@ def main():
                     "mrays_per_s_kernel_only": npx * ph_n.get("raycast", 0) / (ph_ms.get("raycast", 1e-9) * 1e-3) / 1e6,
                     "note": "skip-map build + march; issue/latency bound (ncu: DRAM < 6 % of peak), not an HBM-roofline kernel"},
         "e2e": e2e,
-        # per frame: frame_allocate, select_visible, integrate_carve + skip_prepare, skip_fill, skip_mark, 3 x skip_pass, raycast
-        "gpu_launches": 10 * B * K,
+        # per frame: frame_allocate, select_visible, integrate_carve + skip_fill, skip_mark, 3 x skip_pass, raycast
+        "gpu_launches": 9 * B * K,
         "clocks": sampler.summary(windows[:1]),
         "counters_per_frame": {k: tot[k] / max(tot["frames"], 1) for k in ("n_new", "n_visible", "n_updated", "n_carved", "n_active_post")},
     }

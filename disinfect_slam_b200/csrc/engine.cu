@@ -30,7 +30,7 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 namespace {
-enum { PH_UPLOAD = 0, PH_ALLOC, PH_SELECT, PH_INTEGRATE, PH_RAYCAST, PH_GATHER, PH_SKIPMAP, PH_COUNT };
+enum { PH_UPLOAD = 0, PH_ALLOC, PH_SELECT, PH_INTEGRATE, PH_RAYCAST, PH_GATHER, PH_COUNT };
 
 struct FrameBuf {
   unsigned char* rgb = nullptr; float *depth = nullptr, *ht = nullptr, *lt = nullptr;
@@ -45,7 +45,7 @@ struct tsdf_engine {
   int device = 0, num_sms = 148;
   float voxel_size = 0, truncation = 0;
   tsdf_config cfg{};
-  cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   DeviceState S{};
   FrameBuf fb[2];
   int cur = 0;
@@ -53,10 +53,6 @@ struct tsdf_engine {
   int* visible = nullptr; int* selected = nullptr;
   SkipMap skip{};                    // RayCast empty-space skip map, rebuilt when the block set changed
   uint64_t volume_epoch = 1, skip_epoch = 0;
-  // When the caller alternates Integrate and RayCast, the map of frame k is built on aux_stream right after the
-  // allocation kernel, alongside select + integrate (carving only removes blocks, so the map stays conservative).
-  cudaEvent_t ev_alloc = nullptr, ev_map = nullptr;
-  bool eager_map = false, map_pending = false;
   uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
   float4* gather_out = nullptr; size_t gather_cap = 0; int64_t gather_n = 0;
   int* h_scalar = nullptr;  // pinned scratch (C_COUNT ints)
@@ -143,15 +139,6 @@ static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned c
   phase_begin(e, PH_ALLOC, e->stream);
   launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.tex, e->stream);
   phase_end(e, PH_ALLOC, e->stream);
-  const bool build_now = e->eager_map;
-  if (build_now) {  // every insert of this frame has happened: build the RayCast skip map concurrently
-    cudaEventRecord(e->ev_alloc, e->stream);
-    cudaStreamWaitEvent(e->aux_stream, e->ev_alloc, 0);
-    phase_begin(e, PH_SKIPMAP, e->aux_stream);
-    launch_build_skip_map(e->S, e->skip, e->num_sms, e->aux_stream);
-    phase_end(e, PH_SKIPMAP, e->aux_stream);
-    cudaEventRecord(e->ev_map, e->aux_stream);
-  }
   phase_begin(e, PH_SELECT, e->stream);
   launch_select_visible(e->S, P, e->visible, e->num_sms, e->stream);
   phase_end(e, PH_SELECT, e->stream);
@@ -162,8 +149,6 @@ static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned c
   cudaEventRecord(f.done, e->stream);
   f.in_flight = true;
   e->volume_epoch++;
-  if (build_now) { e->skip_epoch = e->volume_epoch; e->map_pending = true; }
-  e->eager_map = false;
 }
 
 // wait for the frame that used slot `s`, fold its counters into the host mirror, surface errors
@@ -198,7 +183,6 @@ static int drain(tsdf_engine* e) {
   const int first = e->last_slot < 0 ? 0 : 1 - e->last_slot;
   for (int i = 0; i < 2; ++i) { const int r = retire_slot(e, (first + i) & 1); if (r != TSDF_OK) rc = r; }
   CU(cudaStreamSynchronize(e->stream));
-  CU(cudaStreamSynchronize(e->aux_stream));
   return rc;
 }
 
@@ -257,9 +241,6 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
 #define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(TSDF_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); tsdf_destroy(e); return rc_; } } while (0)
   CUX(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUX(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-  CUX(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
-  CUX(cudaEventCreateWithFlags(&e->ev_alloc, cudaEventDisableTiming));
-  CUX(cudaEventCreateWithFlags(&e->ev_map, cudaEventDisableTiming));
   DeviceState& S = e->S;
   S.table_mask = (unsigned)cfg.table_slots - 1; S.pool_blocks = cfg.pool_blocks;
   S.shard_rank = cfg.shard_rank; S.shard_count = cfg.shard_count; S.shard_shift = cfg.flags & TSDF_FLAG_SHARD_SHIFT_MASK;
@@ -297,7 +278,6 @@ int tsdf_destroy(tsdf_handle e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
-  if (e->aux_stream) cudaStreamSynchronize(e->aux_stream);
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
   cudaFree(e->visible); cudaFree(e->selected);
   cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr);
@@ -314,9 +294,6 @@ int tsdf_destroy(tsdf_handle e) {
   for (cudaEvent_t v : e->ev_pool) cudaEventDestroy(v);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-  if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
-  if (e->ev_alloc) cudaEventDestroy(e->ev_alloc);
-  if (e->ev_map) cudaEventDestroy(e->ev_map);
   delete e;
   return TSDF_OK;
 }
@@ -392,14 +369,9 @@ int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const floa
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
   phase_begin(e, PH_RAYCAST, e->stream);
   if (e->skip_epoch != e->volume_epoch) {  // block set may have changed since the map was built
-    if (e->map_pending) { cudaStreamWaitEvent(e->stream, e->ev_map, 0); e->map_pending = false; }  // never overlap two builds
     launch_build_skip_map(e->S, e->skip, e->num_sms, e->stream);
     e->skip_epoch = e->volume_epoch;
-  } else if (e->map_pending) {
-    cudaStreamWaitEvent(e->stream, e->ev_map, 0);
-    e->map_pending = false;
   }
-  e->eager_map = false;  // eager build beside integrate measured no gain: the persistent integrate CTAs hold the whole register file
   launch_raycast(e->S, P, e->truncation / 2, e->skip, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
                  (unsigned long long*)d_packed, e->stream);  // step = truncation / 2, voxel_tsdf.cu:497
   phase_end(e, PH_RAYCAST, e->stream);

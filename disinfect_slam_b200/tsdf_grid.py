@@ -200,7 +200,7 @@ class TSDFGrid:
         ms = np.zeros(8, np.float32)
         cnt = np.zeros(8, np.int64)
         check(self.L.tsdf_get_phase_ms(self.h, _p(ms), _p(cnt)))
-        names = ("upload", "allocate", "select", "integrate", "raycast", "gather", "skipmap")
+        names = ("upload", "allocate", "select", "integrate", "raycast", "gather")
         return {n: float(ms[i]) for i, n in enumerate(names)}, {n: int(cnt[i]) for i, n in enumerate(names)}
 
     def totals(self):

@@ -182,7 +182,7 @@ int tsdf_host_free(void* ptr);
  * on; nothing synchronises until the getters run.  Every retired frame's counters are summed
  * (profiling on or off); tsdf_set_profiling() resets the sums.  out_ms = device milliseconds summed over all calls since
  * then: [0] upload, [1] frame staging + allocate, [2] select visible, [3] integrate + carve,
- * [4] raycast, [5] gather, [6] raycast skip-map build when it runs beside select + integrate; out_count (optional) = number of timed launches per phase.
+ * [4] raycast (skip-map build + march), [5] gather; out_count (optional) = number of timed launches per phase.
  * tsdf_get_totals: sums of the per-frame counters and the number of frames. */
 int tsdf_set_profiling(tsdf_handle h, int enabled);
 int tsdf_get_phase_ms(tsdf_handle h, float out_ms[8], int64_t out_count[8]);
