@@ -485,6 +485,38 @@ def main():
             ph_n[k] = ph_n.get(k, 0) + n[k]
         for k, v in g.totals().items():
             tot[k] = tot.get(k, 0) + v
+    # GatherValid / GatherVoxels on the volumes just built (BASELINE config 5's mesh-export query): selection +
+    # emit kernels timed with CUDA events (result stays on the GPU), then the full call with the D2H of every record
+    gather = None
+    try:
+        for g in engs:
+            g.gather_device(None)  # warm-up: grows the engine's result buffer once
+        for g in engs:
+            g.set_profiling(True)
+        n_vox = {"valid": 0, "bound": 0}
+        bbox = tsdf_grid.BoundingCube(-1.0, 1.0, -1.5, 1.5, -2.0, 2.0)
+        for rep in range(3):
+            for g in engs:
+                n_vox["valid"] = g.gather_device(None)
+        m_valid = sum(g.phase_ms()[0]["gather"] for g in engs) / (3 * len(engs))
+        for g in engs:
+            g.set_profiling(True)
+        for rep in range(3):
+            for g in engs:
+                n_vox["bound"] = g.gather_device(bbox)
+        m_bound = sum(g.phase_ms()[0]["gather"] for g in engs) / (3 * len(engs))
+        t0 = time.perf_counter()
+        rec = engs[0].GatherValid()
+        t_host = time.perf_counter() - t0
+        n_act = engs[0].NumActiveBlock()
+        gb = lambda nv, ms: (8 * n_act + 20 * nv) / (ms * 1e-3) / 1e9 if ms > 0 else None  # noqa: E731
+        gather = {"gather_valid": {"voxels": n_vox["valid"], "device_ms": m_valid, "hbm_gbs": gb(n_vox["valid"], m_valid)},
+                  "gather_in_bound": {"voxels": n_vox["bound"], "device_ms": m_bound, "hbm_gbs": gb(n_vox["bound"], m_bound)},
+                  "gather_valid_to_host": {"voxels": int(len(rec)), "ms": 1e3 * t_host, "d2h_bytes": int(rec.nbytes),
+                                           "note": "pageable numpy destination, includes the 16 B/voxel PCIe copy"},
+                  "bytes_model": "8 B per directory entry + 4 B read + 16 B write per emitted voxel; device_ms includes the selection pass and its 4-byte count read-back"}
+    except Exception as e:  # the gather report is supplementary: never lose the main line over it
+        gather = {"error": repr(e)}
     for g in engs:
         g.close()
     del engs
@@ -589,6 +621,7 @@ def main():
                      "algorithmic_bytes_per_launch": integ_bytes / launches, "us_per_launch": 1e3 * integ_ms / launches,
                      "launches_timed": launches},
         "kernels": kernels,
+        "gather": gather,
         "raycast": {"us_per_view": 1e3 * ph_ms.get("raycast", 0.0) / max(ph_n.get("raycast", 0), 1), "rays_per_view": npx,
                     "mrays_per_s_kernel_only": npx * ph_n.get("raycast", 0) / (ph_ms.get("raycast", 1e-9) * 1e-3) / 1e6,
                     "note": "skip-map build + march; issue/latency bound (ncu: DRAM < 6 % of peak), not an HBM-roofline kernel"},

@@ -169,6 +169,17 @@ class TSDFGrid:
             check(self.L.tsdf_gather_fetch(self.h, _p(out), n.value))
         return out
 
+    def gather_device(self, bbox=None):
+        """Run the selection + emit kernels only; the records stay in the engine's device buffer
+        (tsdf_gather_device_result).  Returns the number of voxels selected."""
+        n = C.c_int64(0)
+        if bbox is None:
+            check(self.L.tsdf_gather_valid(self.h, None, 0, C.byref(n)))
+        else:
+            bb = _f32(tuple(bbox), 6)
+            check(self.L.tsdf_gather_in_bound(self.h, _p(bb), None, 0, C.byref(n)))
+        return int(n.value)
+
     def GatherValid(self):
         return self._gather(None)
 
