@@ -45,6 +45,10 @@ SYMBOLS = {
     "tsdf_raycast": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsdf_raycast_device": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsdf_raycast_resident": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "tsdf_ipc_export": (_i32, [_vp, _vp]),
+    "tsdf_ipc_attach": (_i32, [_vp, _i32, _vp]),
+    "tsdf_peer_attach_local": (_i32, [_vp, _i32, _vp]),
+    "tsdf_raycast_shared": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tsdf_gather_valid": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_in_bound": (_i32, [_vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_fetch": (_i32, [_vp, _vp, _i64]),
@@ -66,6 +70,9 @@ SYMBOLS = {
     "tsdf_get_phase_ms": (_i32, [_vp, _vp, _vp]),
     "tsdf_get_totals": (_i32, [_vp, C.POINTER(Counters), C.POINTER(_i64)]),
 }
+
+
+IPC_BLOB_BYTES = 320
 
 
 def build(force=False):

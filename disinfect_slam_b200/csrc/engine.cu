@@ -52,6 +52,10 @@ struct tsdf_engine {
   int last_slot = -1;  // slot of the most recent frame (its counters are the "last" ones)
   int* visible = nullptr; int* selected = nullptr;
   SkipMap skip{};                    // RayCast empty-space skip map, rebuilt when the block set changed
+  PeerView* d_self = nullptr;        // device copy of this engine's own PeerView (1 entry)
+  PeerView* d_peers = nullptr;       // device array [shard_count]: every shard of a volume sharded over GPUs
+  int n_peers = 0;
+  void* ipc_opened[kMaxPeers][4] = {};  // pointers obtained from cudaIpcOpenMemHandle (closed at destroy)
   uint64_t volume_epoch = 1, skip_epoch = 0;
   uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
   float4* gather_out = nullptr; size_t gather_cap = 0; int64_t gather_n = 0;
@@ -251,6 +255,11 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   CUX(cudaMalloc(&S.ctr, sizeof(int) * C_COUNT));
   CUX(cudaMalloc(&e->visible, sizeof(int) * (size_t)cfg.pool_blocks));
   CUX(cudaMalloc(&e->selected, sizeof(int) * (size_t)cfg.pool_blocks));
+  CUX(cudaMalloc(&e->d_self, sizeof(PeerView))); CUX(cudaMalloc(&e->d_peers, sizeof(PeerView) * kMaxPeers));
+  {
+    PeerView v{}; v.table = S.table; v.table_mask = S.table_mask; v.block_key = S.block_key; v.voxels = S.voxels; v.ctr = S.ctr;
+    CUX(cudaMemcpyAsync(e->d_self, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
+  }
   CUX(cudaMalloc(&e->skip.dist, kSkipMaxCells)); CUX(cudaMalloc(&e->skip.scratch, kSkipMaxCells));
   CUX(cudaMalloc(&e->skip.hdr, sizeof(int) * 8));
   const size_t npx = (size_t)cfg.max_image_pixels;
@@ -281,6 +290,8 @@ int tsdf_destroy(tsdf_handle e) {
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
   cudaFree(e->visible); cudaFree(e->selected);
   cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr);
+  for (int r = 0; r < kMaxPeers; ++r) for (int k = 0; k < 4; ++k) if (e->ipc_opened[r][k]) cudaIpcCloseMemHandle(e->ipc_opened[r][k]);
+  cudaFree(e->d_self); cudaFree(e->d_peers);
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
     cudaFree(f.rgb); cudaFree(f.depth); cudaFree(f.ht); cudaFree(f.lt); cudaFree(f.tex);
@@ -369,7 +380,7 @@ int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const floa
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
   phase_begin(e, PH_RAYCAST, e->stream);
   if (e->skip_epoch != e->volume_epoch) {  // block set may have changed since the map was built
-    launch_build_skip_map(e->S, e->skip, e->num_sms, e->stream);
+    launch_build_skip_map(e->d_self, 1, e->skip, e->num_sms, e->stream);
     e->skip_epoch = e->volume_epoch;
   }
   launch_raycast(e->S, P, e->truncation / 2, e->skip, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
@@ -402,6 +413,100 @@ int tsdf_raycast_resident(tsdf_handle e, float max_depth, int w, int h, const fl
   if (d_rgba) *d_rgba = e->rgba;
   if (d_normal) *d_normal = e->normal;
   if (d_hit_depth) *d_hit_depth = e->hit_depth;
+  return TSDF_OK;
+}
+
+// ---- shared-volume RayCast: a volume sharded over several engines, each reading the others' memory ----------------
+namespace {
+struct IpcBlob {
+  cudaIpcMemHandle_t table, block_key, voxels, ctr;
+  uint32_t table_mask; int32_t pool_blocks, shard_rank, shard_count, shard_shift, device;
+};
+static_assert(sizeof(IpcBlob) <= TSDF_IPC_BLOB_BYTES, "TSDF_IPC_BLOB_BYTES too small");
+}  // namespace
+
+int tsdf_ipc_export(tsdf_handle e, void* blob) {
+  if (!e || !blob) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaSetDevice(e->device));
+  IpcBlob b{};
+  CU(cudaIpcGetMemHandle(&b.table, e->S.table)); CU(cudaIpcGetMemHandle(&b.block_key, e->S.block_key));
+  CU(cudaIpcGetMemHandle(&b.voxels, e->S.voxels)); CU(cudaIpcGetMemHandle(&b.ctr, e->S.ctr));
+  b.table_mask = e->S.table_mask; b.pool_blocks = e->S.pool_blocks; b.shard_rank = e->S.shard_rank;
+  b.shard_count = e->S.shard_count; b.shard_shift = e->S.shard_shift; b.device = e->device;
+  memset(blob, 0, TSDF_IPC_BLOB_BYTES);
+  memcpy(blob, &b, sizeof(b));
+  return TSDF_OK;
+}
+
+static int check_peer_count(tsdf_engine* e, int world) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if (world != e->S.shard_count || world < 1 || world > kMaxPeers)
+    return fail(TSDF_E_INVALID, "peer count %d must equal shard_count %d (at most %d)", world, e->S.shard_count, kMaxPeers);
+  return TSDF_OK;
+}
+static PeerView self_view(const tsdf_engine* e) {
+  PeerView v{}; v.table = e->S.table; v.table_mask = e->S.table_mask; v.block_key = e->S.block_key; v.voxels = e->S.voxels; v.ctr = e->S.ctr;
+  return v;
+}
+
+int tsdf_ipc_attach(tsdf_handle e, int world, const void* blobs) {
+  int rc = check_peer_count(e, world);
+  if (rc) return rc;
+  if (!blobs) return fail(TSDF_E_INVALID, "null blobs");
+  CU(cudaSetDevice(e->device));
+  PeerView views[kMaxPeers] = {};
+  for (int r = 0; r < world; ++r) {
+    IpcBlob b;
+    memcpy(&b, (const char*)blobs + (size_t)r * TSDF_IPC_BLOB_BYTES, sizeof(b));
+    if (b.shard_rank != r || b.shard_count != world || b.shard_shift != e->S.shard_shift)
+      return fail(TSDF_E_INVALID, "blob %d describes shard %d of %d (shift %d)", r, b.shard_rank, b.shard_count, b.shard_shift);
+    if (r == e->S.shard_rank) { views[r] = self_view(e); continue; }
+    void* p[4] = {};
+    const cudaIpcMemHandle_t* hs[4] = {&b.table, &b.block_key, &b.voxels, &b.ctr};
+    for (int k = 0; k < 4; ++k) {
+      if (e->ipc_opened[r][k]) { cudaIpcCloseMemHandle(e->ipc_opened[r][k]); e->ipc_opened[r][k] = nullptr; }
+      CU(cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess));
+      e->ipc_opened[r][k] = p[k];
+    }
+    views[r].table = (const Slot*)p[0]; views[r].table_mask = b.table_mask; views[r].block_key = (const u64*)p[1];
+    views[r].voxels = (const unsigned char*)p[2]; views[r].ctr = (const int*)p[3];
+  }
+  CU(cudaMemcpy(e->d_peers, views, sizeof(PeerView) * world, cudaMemcpyHostToDevice));
+  e->n_peers = world;
+  return TSDF_OK;
+}
+
+int tsdf_peer_attach_local(tsdf_handle e, int world, const tsdf_handle* shards) {
+  int rc = check_peer_count(e, world);
+  if (rc) return rc;
+  if (!shards) return fail(TSDF_E_INVALID, "null shard list");
+  CU(cudaSetDevice(e->device));
+  PeerView views[kMaxPeers] = {};
+  for (int r = 0; r < world; ++r) {
+    const tsdf_engine* o = shards[r];
+    if (!o || o->S.shard_rank != r || o->S.shard_count != world || o->S.shard_shift != e->S.shard_shift || o->device != e->device)
+      return fail(TSDF_E_INVALID, "shard %d: not shard %d of %d on this device with the same granularity", r, r, world);
+    views[r] = self_view(o);
+  }
+  CU(cudaMemcpy(e->d_peers, views, sizeof(PeerView) * world, cudaMemcpyHostToDevice));
+  e->n_peers = world;
+  return TSDF_OK;
+}
+
+int tsdf_raycast_shared(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                        int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth) {
+  if (!e || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
+  if (e->n_peers < 1) return fail(TSDF_E_INVALID, "no peers attached (tsdf_ipc_attach / tsdf_peer_attach_local)");
+  if (w <= 0 || h <= 0 || row0 < 0 || rows < 0) return fail(TSDF_E_INVALID, "bad image size / row range");
+  CU(cudaSetDevice(e->device));
+  const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
+  phase_begin(e, PH_RAYCAST, e->stream);
+  launch_build_skip_map(e->d_peers, e->n_peers, e->skip, e->num_sms, e->stream);  // union of every shard's blocks
+  e->skip_epoch = 0;  // the map no longer describes this engine alone
+  launch_raycast_shared(e->d_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0),
+                        (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, e->stream);
+  phase_end(e, PH_RAYCAST, e->stream);
+  CU(cudaGetLastError());
   return TSDF_OK;
 }
 

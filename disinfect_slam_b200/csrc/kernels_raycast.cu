@@ -27,9 +27,15 @@ namespace tsdf {
 // ------------------------------------------------------------------------------------------
 // header from the AABB counters + fill with the cap.  Every thread derives the same header (a handful of integer
 // operations) so that no separate one-thread launch is needed; thread 0 publishes it for the later kernels.
-__global__ void __launch_bounds__(256) skip_fill_kernel(DeviceState S, SkipMap M) {
-  const int x0 = S.ctr[C_MIN_X], y0 = S.ctr[C_MIN_Y], z0 = S.ctr[C_MIN_Z];
-  const int x1 = S.ctr[C_MAX_X], y1 = S.ctr[C_MAX_Y], z1 = S.ctr[C_MAX_Z];
+__global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M) {
+  // AABB of every shard's inserts (one shard = the engine itself; several = a volume sharded over GPUs, whose
+  // counters are read over NVLink)
+  int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, z0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF, y1 = -0x7FFFFFFF, z1 = -0x7FFFFFFF;
+  for (int r = 0; r < n_shards; ++r) {
+    const int* c = shards[r].ctr;
+    x0 = min(x0, c[C_MIN_X]); y0 = min(y0, c[C_MIN_Y]); z0 = min(z0, c[C_MIN_Z]);
+    x1 = max(x1, c[C_MAX_X]); y1 = max(y1, c[C_MAX_Y]); z1 = max(z1, c[C_MAX_Z]);
+  }
   int shift = 0, n = 0;
   long long nx = 0, ny = 0, nz = 0;
   if (x1 >= x0) {
@@ -49,15 +55,18 @@ __global__ void __launch_bounds__(256) skip_fill_kernel(DeviceState S, SkipMap M
     reinterpret_cast<uint4*>(M.dist)[i] = cap16;
 }
 
-__global__ void __launch_bounds__(256) skip_mark_kernel(DeviceState S, SkipMap M) {
-  const int hw = S.ctr[C_HIGH_WATER];
+__global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M) {
   const int ox = M.hdr[0], oy = M.hdr[1], oz = M.hdr[2], nx = M.hdr[3], ny = M.hdr[4], shift = M.hdr[6];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
-    const u64 k = S.block_key[i];
-    if (k == kEmpty) continue;
-    int bx, by, bz; unpack_key(k, bx, by, bz);
-    const int cx = (bx - ox) >> shift, cy = (by - oy) >> shift, cz = (bz - oz) >> shift;
-    M.dist[((size_t)cz * ny + cy) * nx + cx] = 0;
+  for (int r = 0; r < n_shards; ++r) {
+    const int hw = shards[r].ctr[C_HIGH_WATER];
+    const u64* dir = shards[r].block_key;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+      const u64 k = dir[i];
+      if (k == kEmpty) continue;
+      int bx, by, bz; unpack_key(k, bx, by, bz);
+      const int cx = (bx - ox) >> shift, cy = (by - oy) >> shift, cz = (bz - oz) >> shift;
+      M.dist[((size_t)cz * ny + cy) * nx + cx] = 0;
+    }
   }
 }
 
@@ -85,9 +94,9 @@ __global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigne
   }
 }
 
-void launch_build_skip_map(const DeviceState& S, const SkipMap& M, int num_sms, cudaStream_t st) {
-  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(S, M);
-  skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(S, M);
+void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int num_sms, cudaStream_t st) {
+  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(shards, n_shards, M);
+  skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(shards, n_shards, M);
   skip_pass_kernel<0><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch);
   skip_pass_kernel<1><<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist);
   skip_pass_kernel<2><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch);
@@ -98,7 +107,30 @@ void launch_build_skip_map(const DeviceState& S, const SkipMap& M, int num_sms, 
 // ray march
 // ------------------------------------------------------------------------------------------
 struct Grid { int ox, oy, oz, nx, ny, nz, shift; const unsigned char* dist; };
-struct BlockCache { int bx, by, bz, idx; };  // bx = INT_MIN: nothing cached
+struct BlockCache { int bx, by, bz; const unsigned char* base; };  // bx = INT_MIN: nothing cached; base = null: absent
+
+// Where the voxels of a block live.  Local: this engine's table and pool.  Shared: the table and pool of the shard
+// that owns the block coordinate (owner_of), reached through peer-mapped pointers -- NVLink loads inside the march.
+template <bool SHARED> struct Volume;
+template <> struct Volume<false> {
+  DeviceState S;
+  __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
+    const int idx = table_find(S, pack_key(bx, by, bz));
+    return idx < 0 ? nullptr : S.voxels + (size_t)idx * kBlockBytes;
+  }
+};
+template <> struct Volume<true> {
+  const PeerView* shards; int n_shards, shard_shift;
+  __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
+    const u64 key = pack_key(bx, by, bz);
+    const PeerView& v = shards[owner_of(key, n_shards, shard_shift)];
+    const int idx = table_find_in(v.table, v.table_mask, key);
+    return idx < 0 ? nullptr : v.voxels + (size_t)idx * kBlockBytes;
+  }
+};
+__device__ __forceinline__ const float* base_tsdf(const unsigned char* b) { return reinterpret_cast<const float*>(b); }
+__device__ __forceinline__ const uint32_t* base_rgbw(const unsigned char* b) { return reinterpret_cast<const uint32_t*>(b + kPlaneBytes); }
+__device__ __forceinline__ const float* base_logit(const unsigned char* b) { return reinterpret_cast<const float*>(b + 2 * kPlaneBytes); }
 
 // Chebyshev distance (cells) from block (bx,by,bz) to the nearest cell holding an active block;
 // 0 = this cell holds one (the block itself may still be absent when shift > 0)
@@ -113,29 +145,32 @@ __device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int 
   return max(gx, max(gy, gz));
 }
 
-__device__ __forceinline__ void cache_lookup(const DeviceState& S, const Grid& G, BlockCache& c, int px, int py, int pz) {
+template <class V>
+__device__ __forceinline__ void cache_lookup(const V& vol, const Grid& G, BlockCache& c, int px, int py, int pz) {
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
   if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
     c.bx = bx; c.by = by; c.bz = bz;
-    c.idx = cell_distance(G, bx, by, bz) == 0 ? table_find(S, pack_key(bx, by, bz)) : -1;
+    c.base = cell_distance(G, bx, by, bz) == 0 ? vol.find(bx, by, bz) : nullptr;
   }
 }
 // Retrieve<VoxelTSDF>: absent -> VoxelTSDF() == +1 (voxel_types.cu:8)
-__device__ __forceinline__ float fetch_tsdf(const DeviceState& S, const Grid& G, BlockCache& c, int px, int py, int pz) {
-  cache_lookup(S, G, c, px, py, pz);
-  if (c.idx < 0) return 1.f;
-  return __ldg(block_tsdf(S, c.idx) + voxel_index(px, py, pz));
+template <class V>
+__device__ __forceinline__ float fetch_tsdf(const V& vol, const Grid& G, BlockCache& c, int px, int py, int pz) {
+  cache_lookup(vol, G, c, px, py, pz);
+  if (!c.base) return 1.f;
+  return __ldg(base_tsdf(c.base) + voxel_index(px, py, pz));
 }
-__device__ __forceinline__ float fetch_tsdf_f(const DeviceState& S, const Grid& G, BlockCache& c, float3 p) {
-  return fetch_tsdf(S, G, c, round_to_voxel(p.x), round_to_voxel(p.y), round_to_voxel(p.z));
+template <class V>
+__device__ __forceinline__ float fetch_tsdf_f(const V& vol, const Grid& G, BlockCache& c, float3 p) {
+  return fetch_tsdf(vol, G, c, round_to_voxel(p.x), round_to_voxel(p.y), round_to_voxel(p.z));
 }
 
 // One march sample: TSDF at the voxel nearest to p and `skip` = how many of the FOLLOWING samples are
 // guaranteed to land in unallocated space.  With d = distance of p's cell and cs voxels per cell,
 // every voxel within Chebyshev radius (d-1)*cs of p is unallocated; m further steps move the rounded
 // voxel by at most m*smax + 1 (+1 slack for float accumulation), so m = floor(((d-1)*cs - 2) / smax).
-__device__ __forceinline__ float march_sample(const DeviceState& S, const Grid& G, BlockCache& c, float3 p,
-                                              float inv_smax, int& skip) {
+template <class V>
+__device__ __forceinline__ float march_sample(const V& vol, const Grid& G, BlockCache& c, float3 p, float inv_smax, int& skip) {
   const int px = round_to_voxel(p.x), py = round_to_voxel(p.y), pz = round_to_voxel(p.z);
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
   skip = 0;
@@ -143,28 +178,30 @@ __device__ __forceinline__ float march_sample(const DeviceState& S, const Grid& 
     c.bx = bx; c.by = by; c.bz = bz;
     const int d = cell_distance(G, bx, by, bz);
     if (d == 0) {
-      c.idx = table_find(S, pack_key(bx, by, bz));
+      c.base = vol.find(bx, by, bz);
     } else {
-      c.idx = -1;
+      c.base = nullptr;
       if (d >= 2) skip = __float2int_rd((float)(((d - 1) << (3 + G.shift)) - 2) * inv_smax);
       return 1.f;
     }
   }
-  if (c.idx < 0) return 1.f;
-  return __ldg(block_tsdf(S, c.idx) + voxel_index(px, py, pz));
+  if (!c.base) return 1.f;
+  return __ldg(base_tsdf(c.base) + voxel_index(px, py, pz));
 }
 
 __device__ __forceinline__ unsigned char f2u8(float f) { return (unsigned char)min(255, max(0, __float2int_rz(f))); }
 __device__ __forceinline__ float3 add3(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 
-__global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams P, float step_size, SkipMap M,
-                                                      uchar4* __restrict__ img_rgba, uchar4* __restrict__ img_normal,
+template <bool SHARED>
+__global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameParams P, float step_size, SkipMap M, int row0,
+                                                      int rows, uchar4* __restrict__ img_rgba, uchar4* __restrict__ img_normal,
                                                       float* __restrict__ img_depth, u64* __restrict__ packed) {
-  // CTA = 32 x 8 pixels, warp = 8 x 4 pixels: neighbouring rays walk the same cells and blocks
+  // CTA = 32 x 8 pixels, warp = 8 x 4 pixels: neighbouring rays walk the same cells and blocks; the launch covers
+  // image rows [row0, row0 + rows)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-  const int y = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
-  if (x >= P.w || y >= P.h) return;
+  const int y = row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+  if (x >= P.w || y >= P.h || y >= row0 + rows) return;
   const int idx = y * P.w + x;
   Grid G;
   G.ox = M.hdr[0]; G.oy = M.hdr[1]; G.oz = M.hdr[2]; G.nx = M.hdr[3]; G.ny = M.hdr[4]; G.nz = M.hdr[5]; G.shift = M.hdr[6];
@@ -196,9 +233,9 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
   const float smax = fmaxf(fmaxf(fabsf(ray_step_grid.x), fabsf(ray_step_grid.y)), fabsf(ray_step_grid.z));
   const float inv_smax = 1.f / (smax * 1.001f + 1e-6f);
 
-  BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.idx = -1;
+  BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.base = nullptr;
   int skip;
-  float tsdf_prev = march_sample(S, G, cache, pos_grid, inv_smax, skip);
+  float tsdf_prev = march_sample(vol, G, cache, pos_grid, inv_smax, skip);
   pos_grid = add3(pos_grid, ray_step_grid);
   int i = 1;
 
@@ -214,7 +251,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
       i += k;
     }
     if (i >= max_step) break;
-    const float tsdf_curr = march_sample(S, G, cache, pos_grid, inv_smax, skip);
+    const float tsdf_curr = march_sample(vol, G, cache, pos_grid, inv_smax, skip);
     // ray hit front surface (voxel_tsdf.cu:260)
     if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) { hit = true; break; }
     tsdf_prev = tsdf_curr;
@@ -232,39 +269,39 @@ __global__ void __launch_bounds__(256) raycast_kernel(DeviceState S, FrameParams
     for (;;) {
       const float3 dd = f3(pos1.x - pos2.x, pos1.y - pos2.y, pos1.z - pos2.z);
       if (!(dot3(dd, dd) >= 0.1f)) break;
-      const float tm = fetch_tsdf_f(S, G, cache, mid);
+      const float tm = fetch_tsdf_f(vol, G, cache, mid);
       if (tm < 0) pos2 = mid; else pos1 = mid;
       mid = f3((pos1.x + pos2.x) / 2.f, (pos1.y + pos2.y) / 2.f, (pos1.z + pos2.z) / 2.f);
     }
     const int fx = round_to_voxel(mid.x), fy = round_to_voxel(mid.y), fz = round_to_voxel(mid.z);
-    cache_lookup(S, G, cache, fx, fy, fz);
-    const int cidx = cache.idx;
-    // Block index of each of the 6 neighbours first (only a neighbour across a block face needs a table lookup,
+    cache_lookup(vol, G, cache, fx, fy, fz);
+    const unsigned char* const cbase = cache.base;
+    // Block of each of the 6 neighbours first (only a neighbour across a block face needs a table lookup,
     // at most one per axis), then all 8 voxel loads of the hit -- colour, logit and the 6 gradient samples -- are
     // independent and in flight together (voxel_tsdf.cu:277-291; short arithmetic wraps like the reference).
     const int nx[6] = {(short)(fx + 1), (short)(fx - 1), fx, fx, fx, fx};
     const int ny[6] = {fy, fy, (short)(fy + 1), (short)(fy - 1), fy, fy};
     const int nz[6] = {fz, fz, fz, fz, (short)(fz + 1), (short)(fz - 1)};
-    int nidx[6];
+    const unsigned char* nbase[6];
 #pragma unroll
     for (int n = 0; n < 6; ++n) {
-      nidx[n] = cidx;
+      nbase[n] = cbase;
       if (((nx[n] ^ fx) | (ny[n] ^ fy) | (nz[n] ^ fz)) >> 3) {  // different block coordinate
         const int bx = nx[n] >> 3, by = ny[n] >> 3, bz = nz[n] >> 3;
-        nidx[n] = cell_distance(G, bx, by, bz) == 0 ? table_find(S, pack_key(bx, by, bz)) : -1;
+        nbase[n] = cell_distance(G, bx, by, bz) == 0 ? vol.find(bx, by, bz) : nullptr;
       }
     }
     uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
     float lgt = 0.f;
-    if (cidx >= 0) {
+    if (cbase) {
       const int k = voxel_index(fx, fy, fz);
-      rgbw = __ldg(block_rgbw(S, cidx) + k);
-      lgt = __ldg(block_logit(S, cidx) + k);
+      rgbw = __ldg(base_rgbw(cbase) + k);
+      lgt = __ldg(base_logit(cbase) + k);
     }
     float gv[6];
 #pragma unroll
-    for (int n = 0; n < 6; ++n) gv[n] = nidx[n] >= 0 ? __ldg(block_tsdf(S, nidx[n]) + voxel_index(nx[n], ny[n], nz[n])) : 1.f;
-    const float prob = cidx >= 0 ? logit_to_prob(lgt) : 0.f;
+    for (int n = 0; n < 6; ++n) gv[n] = nbase[n] ? __ldg(base_tsdf(nbase[n]) + voxel_index(nx[n], ny[n], nz[n])) : 1.f;
+    const float prob = cbase ? logit_to_prob(lgt) : 0.f;
     const float gxp = gv[0], gxn = gv[1], gyp = gv[2], gyn = gv[3], gzp = gv[4], gzn = gv[5];
     const float3 nrm = f3(gxp - gxn, gyp - gyn, gzp - gzn);
     const float3 neg_dir = f3(-ray_dir_world.x, -ray_dir_world.y, -ray_dir_world.z);
@@ -295,7 +332,22 @@ void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size,
   dim3 grid((P.w + 31) / 32, (P.h + 7) / 8);
   SkipMap R = M;  // launch_build_skip_map leaves the final distances in `scratch`
   R.dist = M.scratch; R.scratch = M.dist;
-  raycast_kernel<<<grid, 256, 0, st>>>(S, P, step_size, R, rgba, normal, hit_depth, packed_keys);
+  Volume<false> vol; vol.S = S;
+  raycast_kernel<false><<<grid, 256, 0, st>>>(vol, P, step_size, R, 0, P.h, rgba, normal, hit_depth, packed_keys);
+}
+
+// Rows [row0, row0 + rows) of a view over a volume sharded across `n_shards` engines whose tables and pools are
+// mapped in `shards` (device array): bit-identical to the single-volume render, voxels of foreign blocks are read
+// from their owner over NVLink.
+void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
+                           const SkipMap& M, int row0, int rows, uchar4* rgba, uchar4* normal, float* hit_depth,
+                           cudaStream_t st) {
+  if (rows <= 0) return;
+  dim3 grid((P.w + 31) / 32, (rows + 7) / 8);
+  SkipMap R = M;
+  R.dist = M.scratch; R.scratch = M.dist;
+  Volume<true> vol; vol.shards = shards; vol.n_shards = n_shards; vol.shard_shift = shard_shift;
+  raycast_kernel<true><<<grid, 256, 0, st>>>(vol, P, step_size, R, row0, rows, rgba, normal, hit_depth, nullptr);
 }
 
 }  // namespace tsdf

@@ -9,7 +9,10 @@ One process per GPU.  Every rank owns the blocks whose super-block coordinate ha
                 integrates only the blocks it owns -- no further communication.
   RayCast       every rank marches all rays against its shard (foreign space reads as unallocated) and
                 emits per ray two keys  float_bits(hit_depth) << 32 | colour ; one MIN all-reduce merges
-                them by nearest hit (a miss carries +inf).
+                them by nearest hit (a miss carries +inf).  Cheap, but not exact where a hit straddles shards.
+  RayCastExact  every rank renders 1/N of the image rows over the WHOLE volume: the shards' tables and pools are
+                mapped into every process (CUDA IPC) and foreign blocks are read over NVLink inside the march
+                kernel (tsdf_raycast_shared); bit-identical to a single-GPU render; one all-gather of the tiles.
   Gather*       every rank gathers its own blocks; the records are collected on the root (sizes first).
   NumActive     SUM all-reduce.
 
@@ -53,6 +56,40 @@ class EngineBackend:
                                        shard_shift=shard_shift, **kw)
         self._keys = None
         self.ext = torch.cuda.ExternalStream(self.grid.stream(), device=self.device)  # the engine's own stream
+        self._img = {}
+        self._attached = False
+
+    def attach_peers(self, group, world):
+        """Exchange the CUDA IPC handles of every shard's table / pool and map them (once)."""
+        if self._attached:
+            return
+        mine = torch.from_numpy(self.grid.ipc_export()).to(self.device)
+        blobs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(blobs, mine, group=group)
+        self.grid.ipc_attach(torch.stack(blobs).cpu().numpy())
+        self._attached = True
+
+    def raycast_tile(self, max_depth, w, h, K, q, t, rank, world, group):
+        """Rows [rank * rows, (rank + 1) * rows) of the view over the whole sharded volume, gathered on every rank.
+        Everything is enqueued on the engine stream: the 1-element all-reduce in front is the device-side barrier
+        that orders every shard's Integrate before any peer reads its voxels, the all-gather behind orders every
+        peer's reads before the next Integrate."""
+        rows = (h + world - 1) // world
+        key = (w, h, world)
+        if key not in self._img:
+            mk = lambda *shape, dt: (torch.zeros(shape, dtype=dt, device=self.device), torch.zeros(shape, dtype=dt, device=self.device))  # noqa: E731
+            self._img[key] = dict(rgba=mk(world * rows, w, 4, dt=torch.uint8), normal=mk(world * rows, w, 4, dt=torch.uint8),
+                                  depth=mk(world * rows, w, dt=torch.float32), flag=torch.zeros(1, dtype=torch.int32, device=self.device))
+        im = self._img[key]
+        cam = tsdf_grid.CameraParams(K, h, w)
+        with torch.cuda.stream(self.ext):
+            dist.all_reduce(im["flag"], group=group)
+            self.grid.RayCastShared(max_depth, cam, (q, t), rank * rows, rows, im["rgba"][0].data_ptr(), im["normal"][0].data_ptr(),
+                                    im["depth"][0].data_ptr())
+            for k in ("rgba", "normal", "depth"):
+                local, full = im[k]
+                dist.all_gather_into_tensor(full, local[rank * rows:(rank + 1) * rows], group=group)
+        return im["rgba"][1][:h], im["normal"][1][:h], im["depth"][1][:h]
 
     def integrate(self, planes, w, h, max_depth, K, q, t):
         ev = torch.cuda.Event()  # the broadcast ran on torch's stream: the engine stream waits for it on the device
@@ -141,6 +178,19 @@ class ShardedTSDFGrid:
         if self.world > 1:
             dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=self.group)  # nearest hit wins
         return keys
+
+    def RayCastExact(self, max_depth, virtual_cam, cam_T_world, to_host=True):
+        """Same camera on every rank; each rank renders 1/N of the rows over the whole volume (peer memory over
+        NVLink) -- bit-identical to a single-GPU RayCast.  Returns (rgba, normal, hit_depth) on every rank."""
+        q, t = cam_T_world
+        h, w = int(virtual_cam.img_h), int(virtual_cam.img_w)
+        self.backend.attach_peers(self.group, self.world)
+        rgba, normal, depth = self.backend.raycast_tile(max_depth, w, h, np.asarray(virtual_cam.intrinsics, np.float32),
+                                                        np.asarray(q, np.float32), np.asarray(t, np.float32), self.rank, self.world, self.group)
+        if not to_host:
+            return rgba, normal, depth
+        self.backend.synchronize()
+        return rgba.cpu().numpy(), normal.cpu().numpy(), depth.cpu().numpy()
 
     def RayCast(self, max_depth, virtual_cam, cam_T_world):
         """Same camera on every rank; returns (rgba, normal, hit_depth) on every rank."""

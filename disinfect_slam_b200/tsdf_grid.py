@@ -156,6 +156,26 @@ class TSDFGrid:
         check(self.L.tsdf_raycast_device(self.h, max_depth, int(virtual_cam.img_w), int(virtual_cam.img_h), _p(K),
                                          _p(q), _p(t), d_rgba, d_normal, d_depth, d_packed))
 
+    # ---- shared-volume RayCast (volume sharded over several engines) --------------------------------------
+    def ipc_export(self):
+        blob = np.zeros(_lib.IPC_BLOB_BYTES, np.uint8)
+        check(self.L.tsdf_ipc_export(self.h, _p(blob)))
+        return blob
+
+    def ipc_attach(self, blobs):
+        blobs = np.ascontiguousarray(blobs, np.uint8).reshape(-1, _lib.IPC_BLOB_BYTES)
+        check(self.L.tsdf_ipc_attach(self.h, len(blobs), _p(blobs)))
+
+    def peer_attach_local(self, grids):
+        arr = (C.c_void_p * len(grids))(*[g.h for g in grids])
+        check(self.L.tsdf_peer_attach_local(self.h, len(grids), arr))
+
+    def RayCastShared(self, max_depth, virtual_cam, cam_T_world, row0, rows, d_rgba, d_normal, d_depth):
+        K = _f32(virtual_cam.intrinsics, 4)
+        q, t = _pose(cam_T_world)
+        check(self.L.tsdf_raycast_shared(self.h, max_depth, int(virtual_cam.img_w), int(virtual_cam.img_h), _p(K), _p(q), _p(t),
+                                         int(row0), int(rows), d_rgba, d_normal, d_depth))
+
     # ---- TSDFGrid::GatherValid / GatherVoxels (utils/tsdf/voxel_tsdf.cu:399-454) -------------------
     def _gather(self, bbox):
         n = C.c_int64(0)

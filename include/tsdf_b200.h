@@ -128,6 +128,21 @@ int tsdf_raycast_resident(tsdf_handle h, float max_depth, int width, int height,
                           const float q_xyzw[4], const float t_xyz[3], const void** d_rgba, const void** d_normal,
                           const void** d_hit_depth);
 
+/* Shared-volume RayCast for a volume sharded over several engines (no reference counterpart: the reference is
+ * single-GPU).  Every engine exports its table / pool (CUDA IPC, one blob per engine), attaches the blobs of all
+ * shards (index = shard rank; same shard_count and granularity everywhere), and can then render any rows of a
+ * view over the WHOLE volume: blocks of other shards are read from their owner's memory over NVLink inside the
+ * march kernel, so the result is bit-identical to a single-engine render.  The caller must make sure (a barrier)
+ * that no shard is integrating while another one renders.  tsdf_peer_attach_local does the same for engines that
+ * live in one process on one device (tests).  Output pointers are device memory holding the full HxW images;
+ * only rows [row0, row0 + rows) are written.  Asynchronous on the engine stream. */
+#define TSDF_IPC_BLOB_BYTES 320
+int tsdf_ipc_export(tsdf_handle h, void* blob /* TSDF_IPC_BLOB_BYTES */);
+int tsdf_ipc_attach(tsdf_handle h, int shard_count, const void* blobs /* shard_count x TSDF_IPC_BLOB_BYTES */);
+int tsdf_peer_attach_local(tsdf_handle h, int shard_count, const tsdf_handle* shards);
+int tsdf_raycast_shared(tsdf_handle h, float max_depth, int width, int height, const float K[4], const float q_xyzw[4],
+                        const float t_xyz[3], int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth);
+
 /* TSDFGrid::GatherValid()                               utils/tsdf/voxel_tsdf.cu:399-425
  * TSDFGrid::GatherVoxels(BoundingCube<float>)           utils/tsdf/voxel_tsdf.cu:427-454
  * out = array of VoxelSpatialTSDF {float x, y, z, tsdf} (utils/tsdf/voxel_types.cuh:48-57),

@@ -35,10 +35,19 @@ def _worker(rank, world, port, q):
     g.synchronize()
     cam = tsdf_grid.CameraParams(f["K"], cfg.height, cfg.width)
     rgba, normal, depth = g.RayCast(cfg.max_depth, cam, (f["q"], f["t"]))
+    exact = g.RayCastExact(cfg.max_depth, cam, (f["q"], f["t"]))
+    # integrate once more after the peer reads, render again: the stream-ordered barriers must keep this consistent
+    f2 = sc.frame(N_FRAMES)
+    if rank == 0:
+        g.Integrate(f2["rgb"], f2["depth"], f2["ht"], f2["lt"], cfg.max_depth, f2["K"], (f2["q"], f2["t"]))
+    else:
+        g.Integrate(None, None, None, None, None, None, None)
+    exact2 = g.RayCastExact(10.0, cam, (f2["q"], f2["t"]))
     gathered = g.GatherValid()
     n_active = g.NumActiveBlock()
     keys, tsdf, rgbw, prob = g.backend.grid.export()
-    q.put((rank, dict(keys=keys, tsdf=tsdf, rgbw=rgbw, prob=prob, rgba=rgba, normal=normal, depth=depth, gathered=gathered, n_active=n_active)))
+    q.put((rank, dict(keys=keys, tsdf=tsdf, rgbw=rgbw, prob=prob, rgba=rgba, normal=normal, depth=depth, gathered=gathered, n_active=n_active,
+                      exact=exact, exact2=exact2)))
     dist.barrier()
     g.close()
     dist.destroy_process_group()
@@ -66,6 +75,10 @@ def test_two_gpu_sharded_volume_matches_oracle(tsdf_lib):
     for i in range(N_FRAMES):
         f = sc.frame(i)
         o.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"])
+    ref_rc = o.raycast(cfg.max_depth, cfg.width, cfg.height, f["K"], f["q"], f["t"])
+    f2 = sc.frame(N_FRAMES)
+    o.integrate(f2["rgb"], f2["depth"], f2["ht"], f2["lt"], cfg.max_depth, f2["K"], f2["q"], f2["t"])
+    ref_rc2 = o.raycast(10.0, cfg.width, cfg.height, f2["K"], f2["q"], f2["t"])
     ok, ot, oc, op = o.export()
     keys = np.concatenate([res[r]["keys"] for r in range(world)])
     order = compare.key_order(keys)
@@ -79,7 +92,11 @@ def test_two_gpu_sharded_volume_matches_oracle(tsdf_lib):
     assert compare.compare_gather(res[0]["gathered"], o.gather(), "sharded GatherValid")["tsdf_bit_exact"]
     for k in ("rgba", "normal", "depth"):
         assert np.array_equal(res[0][k], res[1][k])
-    rgba, normal, depth, _ = o.raycast(cfg.max_depth, cfg.width, cfg.height, f["K"], f["q"], f["t"])
+    # the exact path (peer memory over NVLink, rows split across the GPUs) reproduces the single-volume render
+    for r in range(world):
+        compare.compare_raycast(res[r]["exact"], ref_rc[:3], f"RayCastExact rank {r}")
+        compare.compare_raycast(res[r]["exact2"], ref_rc2[:3], f"RayCastExact after another Integrate, rank {r}")
+    rgba, normal, depth, _ = ref_rc
     same = (np.isfinite(depth) == np.isfinite(res[0]["depth"])) & ((depth == res[0]["depth"]) | ~np.isfinite(depth))
     print(f"2-GPU min-composited raycast: {1 - same.mean():.4f} of rays differ from the single-volume render (shift {SHIFT})")
     assert 1 - same.mean() < 0.05
