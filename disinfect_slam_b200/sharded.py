@@ -76,20 +76,25 @@ class EngineBackend:
         peer's reads before the next Integrate."""
         rows = (h + world - 1) // world
         key = (w, h, world)
+        tile = rows * w * 4  # bytes of one rank's rows of one 4-byte-per-pixel image
         if key not in self._img:
-            mk = lambda *shape, dt: (torch.zeros(shape, dtype=dt, device=self.device), torch.zeros(shape, dtype=dt, device=self.device))  # noqa: E731
-            self._img[key] = dict(rgba=mk(world * rows, w, 4, dt=torch.uint8), normal=mk(world * rows, w, 4, dt=torch.uint8),
-                                  depth=mk(world * rows, w, dt=torch.float32), flag=torch.zeros(1, dtype=torch.int32, device=self.device))
+            # one packed tile per rank: [rgba rows | normal rows | depth rows], so that ONE all-gather moves all three
+            self._img[key] = dict(local=torch.zeros(3 * tile, dtype=torch.uint8, device=self.device),
+                                  full=torch.zeros(world * 3 * tile, dtype=torch.uint8, device=self.device),
+                                  flag=torch.zeros(1, dtype=torch.int32, device=self.device))
         im = self._img[key]
         cam = tsdf_grid.CameraParams(K, h, w)
+        base = im["local"].data_ptr() - rank * tile  # the kernel indexes whole-image pixels: row0 lands on the tile start
         with torch.cuda.stream(self.ext):
             dist.all_reduce(im["flag"], group=group)
-            self.grid.RayCastShared(max_depth, cam, (q, t), rank * rows, rows, im["rgba"][0].data_ptr(), im["normal"][0].data_ptr(),
-                                    im["depth"][0].data_ptr())
-            for k in ("rgba", "normal", "depth"):
-                local, full = im[k]
-                dist.all_gather_into_tensor(full, local[rank * rows:(rank + 1) * rows], group=group)
-        return im["rgba"][1][:h], im["normal"][1][:h], im["depth"][1][:h]
+            self.grid.RayCastShared(max_depth, cam, (q, t), rank * rows, rows, base, base + tile, base + 2 * tile)
+            dist.all_gather_into_tensor(im["full"], im["local"], group=group)
+            # un-interleave [rank][image][rows] -> three images; these copies must stay on the engine stream too
+            g = im["full"].view(world, 3, tile)
+            rgba = g[:, 0].reshape(world * rows, w, 4)[:h]
+            normal = g[:, 1].reshape(world * rows, w, 4)[:h]
+            depth = g[:, 2].contiguous().view(torch.float32).reshape(world * rows, w)[:h]
+        return rgba, normal, depth
 
     def integrate(self, planes, w, h, max_depth, K, q, t):
         ev = torch.cuda.Event()  # the broadcast ran on torch's stream: the engine stream waits for it on the device

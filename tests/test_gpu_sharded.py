@@ -17,6 +17,14 @@ CFG, N_FRAMES, SHIFT = "small", 4, 2
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception:  # report instead of leaving the parent waiting for its timeout
+        import traceback
+        q.put((rank, {"error": traceback.format_exc()}))
+
+
+def _worker_body(rank, world, port, q):
     import torch.distributed as dist
     from disinfect_slam_b200 import sharded, synth, tsdf_grid
     torch.cuda.set_device(rank)
@@ -65,7 +73,14 @@ def test_two_gpu_sharded_volume_matches_oracle(tsdf_lib):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in range(world))
+    res = {}
+    for _ in range(world):
+        r, d = q.get(timeout=180)
+        if "error" in d:
+            for p in procs:
+                p.kill()
+            pytest.fail(f"rank {r} failed:\n{d['error']}")
+        res[r] = d
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
