@@ -51,6 +51,8 @@ struct tsdf_engine {
   int cur = 0;
   int last_slot = -1;  // slot of the most recent frame (its counters are the "last" ones)
   int* visible = nullptr; int* selected = nullptr;
+  bool blocking_sync = false;
+  cudaEvent_t ev_block = nullptr;
   SkipMap skip{};                    // RayCast empty-space skip map, rebuilt when the block set changed
   PeerView* d_self = nullptr;        // device copy of this engine's own PeerView (1 entry)
   PeerView* d_peers = nullptr;       // device array [shard_count]: every shard of a volume sharded over GPUs
@@ -127,6 +129,15 @@ static void phase_collect(tsdf_engine* e) {
   }
 }
 
+// Host wait for a stream.  Default: cudaStreamSynchronize (spins, lowest latency).  With TSDF_FLAG_BLOCKING_SYNC
+// the wait goes through an event created with cudaEventBlockingSync, which yields the CPU -- for hosts that run
+// more engine threads than they have cores.
+static cudaError_t wait_stream(tsdf_engine* e, cudaStream_t st) {
+  if (!e->blocking_sync) return cudaStreamSynchronize(st);
+  cudaError_t rc = cudaEventRecord(e->ev_block, st);
+  return rc != cudaSuccess ? rc : cudaEventSynchronize(e->ev_block);
+}
+
 static int check_frame_args(tsdf_engine* e, const void* a, const void* b, const void* c, const void* d, int w, int h,
                             const float* K, const float* q, const float* t) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
@@ -186,7 +197,7 @@ static int drain(tsdf_engine* e) {
   // retire in submission order so that `last` ends up describing the newest frame
   const int first = e->last_slot < 0 ? 0 : 1 - e->last_slot;
   for (int i = 0; i < 2; ++i) { const int r = retire_slot(e, (first + i) & 1); if (r != TSDF_OK) rc = r; }
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   return rc;
 }
 
@@ -248,6 +259,8 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   DeviceState& S = e->S;
   S.table_mask = (unsigned)cfg.table_slots - 1; S.pool_blocks = cfg.pool_blocks;
   S.shard_rank = cfg.shard_rank; S.shard_count = cfg.shard_count; S.shard_shift = cfg.flags & TSDF_FLAG_SHARD_SHIFT_MASK;
+  e->blocking_sync = (cfg.flags & TSDF_FLAG_BLOCKING_SYNC) != 0;
+  CUX(cudaEventCreateWithFlags(&e->ev_block, cudaEventDisableTiming | cudaEventBlockingSync));
   CUX(cudaMalloc(&S.table, sizeof(Slot) * (size_t)cfg.table_slots));
   CUX(cudaMalloc(&S.block_key, sizeof(u64) * (size_t)cfg.pool_blocks));
   CUX(cudaMalloc(&S.voxels, (size_t)kBlockBytes * (size_t)cfg.pool_blocks));
@@ -267,8 +280,9 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
     FrameBuf& f = e->fb[i];
     CUX(cudaMalloc(&f.rgb, 3 * npx)); CUX(cudaMalloc(&f.depth, 4 * npx)); CUX(cudaMalloc(&f.ht, 4 * npx)); CUX(cudaMalloc(&f.lt, 4 * npx));
     CUX(cudaMalloc(&f.tex, sizeof(Texel) * npx));
-    CUX(cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
-    CUX(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    const unsigned evf = cudaEventDisableTiming | (e->blocking_sync ? cudaEventBlockingSync : 0u);
+    CUX(cudaEventCreateWithFlags(&f.uploaded, evf));
+    CUX(cudaEventCreateWithFlags(&f.done, evf));
     CUX(cudaMallocHost(&f.h_ctr, sizeof(int) * C_COUNT));
     memset(f.h_ctr, 0, sizeof(int) * C_COUNT);
   }
@@ -301,6 +315,7 @@ int tsdf_destroy(tsdf_handle e) {
   }
   cudaFree(e->rgba); cudaFree(e->normal); cudaFree(e->hit_depth); cudaFree(e->gather_out);
   if (e->h_scalar) cudaFreeHost(e->h_scalar);
+  if (e->ev_block) cudaEventDestroy(e->ev_block);
   phase_collect(e);
   for (cudaEvent_t v : e->ev_pool) cudaEventDestroy(v);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -400,7 +415,7 @@ int tsdf_raycast(tsdf_handle e, float max_depth, int w, int h, const float K[4],
   if (rgba) CU(cudaMemcpyAsync(rgba, e->rgba, 4 * n, cudaMemcpyDeviceToHost, e->stream));
   if (normal) CU(cudaMemcpyAsync(normal, e->normal, 4 * n, cudaMemcpyDeviceToHost, e->stream));
   if (hit_depth) CU(cudaMemcpyAsync(hit_depth, e->hit_depth, 4 * n, cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   return TSDF_OK;
 }
 
@@ -520,7 +535,7 @@ static int select_blocks(tsdf_engine* e, const float* bbox, int* n_sel) {
   CU(cudaMemsetAsync(e->S.ctr + C_NSEL, 0, sizeof(int), e->stream));
   launch_select_blocks(e->S, bbox != nullptr, g, e->selected, e->num_sms, e->stream);
   CU(cudaMemcpyAsync(e->h_scalar, e->S.ctr + C_NSEL, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   *n_sel = e->h_scalar[0];
   return TSDF_OK;
 }
@@ -550,7 +565,7 @@ static int gather_impl(tsdf_engine* e, const float* bbox, float* out, int64_t ca
     const size_t m = (size_t)std::min<int64_t>(cap, e->gather_n);
     if (m) CU(cudaMemcpyAsync(out, e->gather_out, sizeof(float4) * m, cudaMemcpyDeviceToHost, e->stream));
   }
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   return TSDF_OK;
 }
 int tsdf_gather_valid(tsdf_handle e, float* out, int64_t cap, int64_t* n) { return gather_impl(e, nullptr, out, cap, n); }
@@ -563,7 +578,7 @@ int tsdf_gather_fetch(tsdf_handle e, float* out, int64_t cap) {
   CU(cudaSetDevice(e->device));
   const size_t m = (size_t)std::min<int64_t>(cap, e->gather_n);
   if (m) CU(cudaMemcpyAsync(out, e->gather_out, sizeof(float4) * m, cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   return TSDF_OK;
 }
 int tsdf_gather_device_result(tsdf_handle e, const void** d_out, int64_t* n) {
@@ -579,7 +594,7 @@ int tsdf_num_active_blocks(tsdf_handle e, int* n) {
   int rc = drain(e);
   if (rc) return rc;
   CU(cudaMemcpyAsync(e->h_scalar, e->S.ctr + C_FREE, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   e->n_active = e->cfg.pool_blocks - e->h_scalar[0];
   *n = e->n_active;
   return TSDF_OK;
@@ -604,7 +619,7 @@ uint32_t tsdf_hash(int16_t bx, int16_t by, int16_t bz) { return hash_block(bx, b
 static int after_mutation(tsdf_engine* e) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(e->h_scalar, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   e->n_active = e->cfg.pool_blocks - e->h_scalar[C_FREE];
   if (e->h_scalar[C_ERROR] & ERR_POOL) return fail(TSDF_E_POOL_EXHAUSTED, "voxel block pool exhausted (pool_blocks=%d)", e->cfg.pool_blocks);
   if (e->h_scalar[C_ERROR] & ERR_TABLE) return fail(TSDF_E_TABLE_FULL, "hash table full");
@@ -644,7 +659,7 @@ int tsdf_retrieve_voxels(tsdf_handle e, const int16_t* pts, int n, float* tsdf_o
   if (n && rgbw) CU(cudaMemcpyAsync(rgbw, dc.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
   if (n && prob) CU(cudaMemcpyAsync(prob, dpr.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
   if (n && found) CU(cudaMemcpyAsync(found, df.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   return TSDF_OK;
 }
 int tsdf_assign_voxels(tsdf_handle e, const int16_t* pts, int n, const float* tsdf_in, const uint8_t* rgbw, const float* prob) {
@@ -659,7 +674,7 @@ int tsdf_assign_voxels(tsdf_handle e, const int16_t* pts, int n, const float* ts
   if (n && prob) CU(cudaMemcpyAsync(dpr.p, prob, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
   launch_assign_list(e->S, dp.p, n, tsdf_in ? dt.p : nullptr, rgbw ? dc.p : nullptr, prob ? dpr.p : nullptr, e->stream);
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   return TSDF_OK;
 }
 
@@ -680,7 +695,7 @@ int tsdf_export_blocks(tsdf_handle e, int16_t* keys, float* tsdf_out, uint8_t* r
   CU(cudaMemcpyAsync(hk.data(), dk.p, sizeof(short) * hk.size(), cudaMemcpyDeviceToHost, e->stream));
   std::vector<int> hsel(n);
   CU(cudaMemcpyAsync(hsel.data(), e->selected, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+  CU(wait_stream(e, e->stream));
   std::vector<int> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::sort(order.begin(), order.end(), [&](int a, int b) {
@@ -701,7 +716,7 @@ int tsdf_export_blocks(tsdf_handle e, int16_t* keys, float* tsdf_out, uint8_t* r
     if (tsdf_out) CU(cudaMemcpyAsync(tsdf_out + (size_t)b0 * 512, ct.p, 4 * (size_t)nb * 512, cudaMemcpyDeviceToHost, e->stream));
     if (rgbw) CU(cudaMemcpyAsync(rgbw + (size_t)b0 * 2048, cc.p, 4 * (size_t)nb * 512, cudaMemcpyDeviceToHost, e->stream));
     if (prob) CU(cudaMemcpyAsync(prob + (size_t)b0 * 512, cp.p, 4 * (size_t)nb * 512, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+    CU(wait_stream(e, e->stream));
   }
   return TSDF_OK;
 }
@@ -717,7 +732,7 @@ int tsdf_set_profiling(tsdf_handle e, int enabled) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
   CU(cudaSetDevice(e->device));
   int rc = drain(e); if (rc) return rc;
-  CU(cudaStreamSynchronize(e->copy_stream));
+  CU(wait_stream(e, e->copy_stream));
   phase_collect(e);
   e->profiling = enabled != 0;
   for (int p = 0; p < PH_COUNT; ++p) { e->phase_total_ms[p] = 0.0; e->phase_count[p] = 0; }
@@ -728,7 +743,7 @@ int tsdf_get_phase_ms(tsdf_handle e, float out_ms[8], int64_t out_count[8]) {
   if (!e || !out_ms) return fail(TSDF_E_INVALID, "null argument");
   CU(cudaSetDevice(e->device));
   int rc = drain(e); if (rc) return rc;
-  CU(cudaStreamSynchronize(e->copy_stream));
+  CU(wait_stream(e, e->copy_stream));
   phase_collect(e);
   for (int p = 0; p < 8; ++p) { out_ms[p] = 0.f; if (out_count) out_count[p] = 0; }
   for (int p = 0; p < PH_COUNT; ++p) { out_ms[p] = (float)e->phase_total_ms[p]; if (out_count) out_count[p] = e->phase_count[p]; }

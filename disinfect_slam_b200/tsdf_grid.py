@@ -72,7 +72,7 @@ class PinnedArray:
 
 class TSDFGrid:
     def __init__(self, voxel_size, truncation, pool_blocks=None, table_slots=None, max_image_pixels=None, device=None,
-                 shard_rank=0, shard_count=1, shard_shift=0):
+                 shard_rank=0, shard_count=1, shard_shift=0, blocking_sync=False):
         self.L = _lib.lib()
         self.voxel_size, self.truncation = float(voxel_size), float(truncation)
         cfg = Config()
@@ -88,7 +88,7 @@ class TSDFGrid:
         if device is not None:
             cfg.device = int(device)
         cfg.shard_rank, cfg.shard_count = int(shard_rank), int(shard_count)
-        cfg.flags = int(shard_shift) & 0xF
+        cfg.flags = (int(shard_shift) & 0xF) | (0x10 if blocking_sync else 0)
         self.cfg = cfg
         self.h = C.c_void_p()
         check(self.L.tsdf_create(voxel_size, truncation, C.byref(cfg), C.byref(self.h)))

@@ -47,6 +47,7 @@ typedef struct tsdf_engine* tsdf_handle;
  * (NUM_BLOCK utils/tsdf/voxel_mem.cuh:11-12, NUM_ENTRY utils/tsdf/voxel_hash.cuh:13-25,
  *  MAX_IMG_SIZE utils/tsdf/voxel_tsdf.cu:10-12). */
 #define TSDF_FLAG_SHARD_SHIFT_MASK 0xF
+#define TSDF_FLAG_BLOCKING_SYNC 0x10 /* host waits yield the CPU (cudaEventBlockingSync) instead of spinning */
 
 typedef struct tsdf_config {
   int32_t struct_size;      /* = sizeof(tsdf_config) */
@@ -56,7 +57,8 @@ typedef struct tsdf_config {
   int32_t max_image_pixels; /* largest W*H accepted (default 1920 * 1080) */
   int32_t shard_rank;       /* multi-GPU block ownership: this engine keeps only blocks with */
   int32_t shard_count;      /*   owner(block) == shard_rank of shard_count (default 0 of 1) */
-  int32_t flags;            /* bits 0..3: shard granularity shift s -- (1 << s)^3 neighbouring blocks share an owner */
+  int32_t flags;            /* bits 0..3: shard granularity shift s -- (1 << s)^3 neighbouring blocks share an owner;
+                               TSDF_FLAG_BLOCKING_SYNC */
 } tsdf_config;
 
 /* Counters of the last tsdf_integrate* call (what the reference only logs through
