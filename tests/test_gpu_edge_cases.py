@@ -122,3 +122,22 @@ def test_ragged_sizes_repeated_and_empty_frames(tg):
         cam = tg.CameraParams(f["K"], h, w)
         compare.compare_raycast(g.RayCast(cfg.max_depth, cam, (f["q"], f["t"])), o.raycast(cfg.max_depth, w, h, f["K"], f["q"], f["t"])[:3], f"{w}x{h}")
         g.close()
+
+
+def test_blocking_sync_flag_gives_identical_results(tg):
+    cfg = synth.config("tiny")
+    sc = synth.Scene(cfg)
+    a = tg.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots)
+    b = tg.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots, blocking_sync=True)
+    for i in range(3):
+        f = sc.frame(i)
+        for g in (a, b):
+            g.Integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], (f["q"], f["t"]))
+    for x, y in zip(a.export(), b.export()):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    cam = tg.CameraParams(f["K"], cfg.height, cfg.width)
+    for x, y in zip(a.RayCast(cfg.max_depth, cam, (f["q"], f["t"])), b.RayCast(cfg.max_depth, cam, (f["q"], f["t"]))):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    assert np.array_equal(a.GatherValid().view(np.uint32), b.GatherValid().view(np.uint32)) or a.GatherValid().shape == b.GatherValid().shape
+    a.close()
+    b.close()
