@@ -246,8 +246,13 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   for (;;) {
     if (skip > 0) {  // the next `skip` samples read +1: advance the position exactly as the reference does
       const int k = min(skip, max_step - i);
+      f32x2 pxy = pack2(pos_grid.x, pos_grid.y);  // x and y advance in one FADD2 per step
+      const f32x2 sxy = pack2(ray_step_grid.x, ray_step_grid.y);
+      float pz = pos_grid.z;
 #pragma unroll 8
-      for (int j = 0; j < k; ++j) pos_grid = add3(pos_grid, ray_step_grid);
+      for (int j = 0; j < k; ++j) { pxy = add2(pxy, sxy); pz += ray_step_grid.z; }
+      unpack2(pxy, pos_grid.x, pos_grid.y);
+      pos_grid.z = pz;
       i += k;
     }
     if (i >= max_step) break;
