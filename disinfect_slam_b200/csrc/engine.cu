@@ -97,7 +97,7 @@ static FrameParams make_params(const tsdf_engine* e, int w, int h, float max_dep
   P.world_T_cam = pose_inverse(P.cam_T_world);
   P.K = Intr{K[0], K[1], K[2], K[3]};
   P.Kinv = intr_inverse(P.K);
-  P.w = w; P.h = h; P.max_depth = max_depth; P.voxel_size = e->voxel_size; P.truncation = e->truncation;
+  P.w = w; P.h = h; P.max_depth = max_depth; P.voxel_size = e->voxel_size; P.truncation = e->truncation; P.neg_zero = -0.0f;
   return P;
 }
 static cudaEvent_t ev_get(tsdf_engine* e) {
