@@ -155,10 +155,10 @@ static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned c
   launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.tex, e->stream);
   phase_end(e, PH_ALLOC, e->stream);
   phase_begin(e, PH_SELECT, e->stream);
-  launch_select_visible(e->S, P, e->visible, e->num_sms, e->stream);
+  launch_select_visible(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, e->num_sms, e->stream);
   phase_end(e, PH_SELECT, e->stream);
   phase_begin(e, PH_INTEGRATE, e->stream);
-  launch_integrate_carve(e->S, P, e->visible, f.tex, e->num_sms, e->stream);
+  launch_integrate_carve(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, f.tex, e->num_sms, e->stream);
   phase_end(e, PH_INTEGRATE, e->stream);
   cudaMemcpyAsync(f.h_ctr, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream);
   cudaEventRecord(f.done, e->stream);
@@ -266,7 +266,7 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   CUX(cudaMalloc(&S.voxels, (size_t)kBlockBytes * (size_t)cfg.pool_blocks));
   CUX(cudaMalloc(&S.free_stack, sizeof(int) * (size_t)cfg.pool_blocks));
   CUX(cudaMalloc(&S.ctr, sizeof(int) * C_COUNT));
-  CUX(cudaMalloc(&e->visible, sizeof(int) * (size_t)cfg.pool_blocks));
+  CUX(cudaMalloc(&e->visible, sizeof(int) * 2 * (size_t)cfg.pool_blocks));  // [visible pool indices | per-entry carve state]
   CUX(cudaMalloc(&e->selected, sizeof(int) * (size_t)cfg.pool_blocks));
   CUX(cudaMalloc(&e->d_self, sizeof(PeerView))); CUX(cudaMalloc(&e->d_peers, sizeof(PeerView) * kMaxPeers));
   {

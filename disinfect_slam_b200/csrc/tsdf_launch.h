@@ -9,8 +9,9 @@ namespace tsdf {
 // kernels_integrate.cu
 void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const unsigned char* rgb, const float* depth,
                            const float* ht, const float* lt, Texel* tex, cudaStream_t st);
-void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int num_sms, cudaStream_t st);
-void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, const Texel* tex,
+void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int* vis_state, int num_sms,
+                           cudaStream_t st);
+void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
                             int num_sms, cudaStream_t st);
 
 // kernels_raycast.cu

@@ -18,3 +18,10 @@ g++ -o "$OUT/dropin_tsdf_module" "$OUT/dropin_main.o" "$OUT/tsdf_module.o" "$OUT
     -L"$ROOT/disinfect_slam_b200" -ltsdf_b200 -L/usr/local/cuda/lib64 -lcudart -lpthread \
     -Wl,-rpath,'$ORIGIN/../../../disinfect_slam_b200' -Wl,-rpath,/usr/local/cuda/lib64
 echo "built $OUT/dropin_tsdf_module"
+# the same driver on the B200-native TSDFSystem (include/tsdf_b200/tsdf_system.hpp through the shadowing
+# modules/tsdf_module.h): the reference's tsdf_module.cc is NOT part of this binary
+g++ -O2 -std=c++17 -w -I"$ROOT/include/tsdf_b200/compat_system" $INC -c "$HERE/dropin_main.cc" -o "$OUT/dropin_native_main.o"
+g++ -o "$OUT/dropin_native_system" "$OUT/dropin_native_main.o" "$OUT/voxel_types.o" \
+    -L"$ROOT/disinfect_slam_b200" -ltsdf_b200 -L/usr/local/cuda/lib64 -lcudart -lpthread \
+    -Wl,-rpath,'$ORIGIN/../../../disinfect_slam_b200' -Wl,-rpath,/usr/local/cuda/lib64
+echo "built $OUT/dropin_native_system"

@@ -38,10 +38,21 @@ int main(int argc, char** argv) {
       sys.Integrate(last, cv::Mat(H.h, H.w, CV_8UC3, rgb[i].data()), cv::Mat(H.h, H.w, CV_32FC1, depth[i].data()),
                     cv::Mat(H.h, H.w, CV_32FC1, ht[i].data()), cv::Mat(H.h, H.w, CV_32FC1, lt[i].data()));
     }
-    // TSDFSystem has no flush: wait until two consecutive queries agree after the queue had time to drain
     const BoundingCube<float> box = {H.bbox[0], H.bbox[1], H.bbox[2], H.bbox[3], H.bbox[4], H.bbox[5]};
     std::vector<VoxelSpatialTSDF> out, prev;
-    for (int tries = 0; tries < 100; ++tries) {
+#ifdef TSDF_B200_NATIVE_SYSTEM
+    // the native system: one frame without probability images exercises the cached plane of ones when the frame
+    // file asks for it (pad == 1), then Flush() makes the volume current
+    if (H.pad == 1) sys.Integrate(last, cv::Mat(H.h, H.w, CV_8UC3, rgb.back().data()), cv::Mat(H.h, H.w, CV_32FC1, depth.back().data()));
+    sys.Flush();
+    if (sys.Backlog() != 0 || sys.FramesIntegrated() != H.n_frames + (H.pad == 1 ? 1 : 0)) { fprintf(stderr, "flush left a backlog\n"); return 1; }
+    out = sys.Query(box);
+    const int max_tries = 0;
+#else
+    // the reference's TSDFSystem has no flush: wait until two consecutive queries agree after the queue had time to drain
+    const int max_tries = 100;
+#endif
+    for (int tries = 0; tries < max_tries; ++tries) {
       std::this_thread::sleep_for(std::chrono::milliseconds(300));
       out = sys.Query(box);
       if (tries > 0 && out.size() == prev.size() && !out.empty()) break;

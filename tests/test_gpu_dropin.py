@@ -1,6 +1,9 @@
-"""GPU test of the drop-in boundary: the reference's own TSDFSystem (modules/tsdf_module.cc, compiled
-unmodified by tests/cpp/build_dropin.sh against include/tsdf_b200/compat/utils/tsdf/voxel_tsdf.cuh)
-drives the B200 engine; its Query(bbox) result must equal the oracle's GatherVoxels on the same frames."""
+"""GPU tests of the drop-in boundary.
+(1) the reference's own TSDFSystem (modules/tsdf_module.cc, compiled unmodified by tests/cpp/build_dropin.sh against
+    include/tsdf_b200/compat/utils/tsdf/voxel_tsdf.cuh) drives the B200 engine;
+(2) the B200-native TSDFSystem (include/tsdf_b200/tsdf_system.hpp behind the shadowing modules/tsdf_module.h:
+    pipelined uploads, Flush, cached default probabilities) runs the same driver program.
+In both cases Query(bbox) must equal the oracle's GatherVoxels on the same frames, bit for bit."""
 import os
 import struct
 import subprocess
@@ -14,31 +17,44 @@ from oracle.oracle import Oracle
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(HERE, "cpp", "_build", "dropin_tsdf_module")
+BIN_NATIVE = os.path.join(HERE, "cpp", "_build", "dropin_native_system")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(BIN), reason="tests/cpp/_build not built (needs /root/reference at build time)")]
 
 
-def test_reference_tsdf_system_runs_on_the_engine(tmp_path, tsdf_lib):
+def _run_driver(binary, tmp_path, n_frames, extra_frame_without_probs):
     cfg = synth.config("tiny")
     sc = synth.Scene(cfg)
-    n_frames = 5
     bbox = (-1.5, 1.5, -1.4, 1.0, -2.5, 2.5)
     o = Oracle(cfg.voxel_size, cfg.truncation)
     frames = tmp_path / "frames.bin"
     with open(frames, "wb") as fh:
-        fh.write(struct.pack("<4i3f4f6f", n_frames, cfg.width, cfg.height, 0, cfg.voxel_size, cfg.truncation, cfg.max_depth,
-                             *[float(np.float32(k)) for k in cfg.K], *bbox))
+        fh.write(struct.pack("<4i3f4f6f", n_frames, cfg.width, cfg.height, 1 if extra_frame_without_probs else 0, cfg.voxel_size,
+                             cfg.truncation, cfg.max_depth, *[float(np.float32(k)) for k in cfg.K], *bbox))
         for i in range(n_frames):
             f = sc.frame(i)
             o.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"])
             fh.write(np.concatenate([f["q"], f["t"]]).astype(np.float32).tobytes())
             for k in ("rgb", "depth", "ht", "lt"):
                 fh.write(f[k].tobytes())
+    if extra_frame_without_probs:  # the last frame once more with ht = lt = 1 (tsdf_module.cc:28-33)
+        ones = np.ones_like(f["depth"])
+        o.integrate(f["rgb"], f["depth"], ones, ones, cfg.max_depth, f["K"], f["q"], f["t"])
     out = tmp_path / "out.bin"
-    res = subprocess.run([BIN, str(frames), str(out)], capture_output=True, text=True, timeout=120)
+    res = subprocess.run([binary, str(frames), str(out)], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     raw = open(out, "rb").read()
     n = struct.unpack("<q", raw[:8])[0]
     got = np.frombuffer(raw[8:], np.float32).reshape(n, 4)
-    want = o.gather(bbox)
-    rep = compare.compare_gather(got, want, "TSDFSystem::Query")
+    return compare.compare_gather(got, o.gather(bbox), os.path.basename(binary))
+
+
+def test_reference_tsdf_system_runs_on_the_engine(tmp_path, tsdf_lib):
+    rep = _run_driver(BIN, tmp_path, 5, False)
+    assert rep["tsdf_bit_exact"] and rep["n_voxels"] > 100 * 512
+
+
+@pytest.mark.parametrize("extra", [False, True])
+def test_native_tsdf_system(tmp_path, tsdf_lib, extra):
+    assert os.path.exists(BIN_NATIVE)
+    rep = _run_driver(BIN_NATIVE, tmp_path, 6, extra)
     assert rep["tsdf_bit_exact"] and rep["n_voxels"] > 100 * 512
