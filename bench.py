@@ -525,11 +525,25 @@ def main():
         rec = engs[0].GatherValid()
         t_host = time.perf_counter() - t0
         n_act = engs[0].NumActiveBlock()
+        # mesh extraction on the GPU: what replaces "download every voxel + mesh on one CPU core"
+        for g in engs:
+            g.ExtractMesh(None, to_host=False)  # warm-up: sizes the result buffer
+            g.set_profiling(True)
+        for rep in range(3):
+            for g in engs:
+                n_tri = g.ExtractMesh(None, to_host=False)
+        m_mesh = sum(g.phase_ms()[0]["gather"] for g in engs) / (3 * len(engs))
+        t0 = time.perf_counter()
+        tris = engs[0].ExtractMesh(None)
+        t_mesh_host = time.perf_counter() - t0
         gb = lambda nv, ms: (8 * n_act + 20 * nv) / (ms * 1e-3) / 1e9 if ms > 0 else None  # noqa: E731
         gather = {"gather_valid": {"voxels": n_vox["valid"], "device_ms": m_valid, "hbm_gbs": gb(n_vox["valid"], m_valid)},
                   "gather_in_bound": {"voxels": n_vox["bound"], "device_ms": m_bound, "hbm_gbs": gb(n_vox["bound"], m_bound)},
                   "gather_valid_to_host": {"voxels": int(len(rec)), "ms": 1e3 * t_host, "d2h_bytes": int(rec.nbytes),
                                            "note": "pageable numpy destination, includes the 16 B/voxel PCIe copy"},
+                  "extract_mesh": {"triangles": int(n_tri), "device_ms": m_mesh, "to_host_ms": 1e3 * t_mesh_host, "d2h_bytes": int(tris.nbytes),
+                                   "note": "count + emit kernels over the same block selection as gather_valid (incl. two 8-byte read-backs); "
+                                           "to_host adds the 36 B/triangle copy into a pageable numpy array"},
                   "bytes_model": "8 B per directory entry + 4 B read + 16 B write per emitted voxel; device_ms includes the selection pass and its 4-byte count read-back"}
     except Exception as e:  # the gather report is supplementary: never lose the main line over it
         gather = {"error": repr(e)}

@@ -53,6 +53,9 @@ SYMBOLS = {
     "tsdf_gather_in_bound": (_i32, [_vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_fetch": (_i32, [_vp, _vp, _i64]),
     "tsdf_gather_device_result": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    "tsdf_extract_mesh": (_i32, [_vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    "tsdf_mesh_fetch": (_i32, [_vp, _vp, _i64]),
+    "tsdf_mesh_device_result": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "tsdf_num_active_blocks": (_i32, [_vp, C.POINTER(_i32)]),
     "tsdf_get_counters": (_i32, [_vp, C.POINTER(Counters)]),
     "tsdf_synchronize": (_i32, [_vp]),

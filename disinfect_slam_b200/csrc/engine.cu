@@ -61,6 +61,8 @@ struct tsdf_engine {
   uint64_t volume_epoch = 1, skip_epoch = 0;
   uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
   float4* gather_out = nullptr; size_t gather_cap = 0; int64_t gather_n = 0;
+  float* mesh_out = nullptr; size_t mesh_cap = 0; int64_t mesh_n = 0;  // triangles (9 floats each), grow-only
+  unsigned long long* mesh_counter = nullptr;
   int* h_scalar = nullptr;  // pinned scratch (C_COUNT ints)
   int n_active = 0;         // host mirror after the last completed frame
   tsdf_counters last{};
@@ -302,7 +304,7 @@ int tsdf_destroy(tsdf_handle e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
-  cudaFree(e->visible); cudaFree(e->selected);
+  cudaFree(e->visible); cudaFree(e->selected); cudaFree(e->mesh_out); cudaFree(e->mesh_counter);
   cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr);
   for (int r = 0; r < kMaxPeers; ++r) for (int k = 0; k < 4; ++k) if (e->ipc_opened[r][k]) cudaIpcCloseMemHandle(e->ipc_opened[r][k]);
   cudaFree(e->d_self); cudaFree(e->d_peers);
@@ -585,6 +587,59 @@ int tsdf_gather_device_result(tsdf_handle e, const void** d_out, int64_t* n) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
   if (d_out) *d_out = e->gather_out;
   if (n) *n = e->gather_n;
+  return TSDF_OK;
+}
+
+// ---- mesh extraction (kernels_mesh.cu) --------------------------------------------------
+int tsdf_extract_mesh(tsdf_handle e, const float* bbox, float* out, int64_t cap, int64_t* n_triangles) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  if (rc) return rc;
+  phase_begin(e, PH_GATHER, e->stream);
+  int n_sel = 0;
+  rc = select_blocks(e, bbox, &n_sel);
+  if (rc) return rc;
+  if (!e->mesh_counter) CU(cudaMalloc(&e->mesh_counter, sizeof(unsigned long long)));
+  // pass 1: count (the same kernel without the writes), pass 2: emit into the grow-only result buffer
+  CU(cudaMemsetAsync(e->mesh_counter, 0, sizeof(unsigned long long), e->stream));
+  launch_mesh_count(e->S, e->selected, n_sel, e->voxel_size, e->mesh_counter, e->stream);
+  static_assert(sizeof(unsigned long long) <= sizeof(int) * 2, "h_scalar scratch");
+  CU(cudaMemcpyAsync(e->h_scalar, e->mesh_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CU(wait_stream(e, e->stream));
+  unsigned long long total = 0;
+  memcpy(&total, e->h_scalar, sizeof(total));
+  if ((size_t)total > e->mesh_cap) {
+    cudaFree(e->mesh_out); e->mesh_out = nullptr; e->mesh_cap = 0;
+    const size_t want = std::max((size_t)total, (size_t)1 << 18);
+    CU(cudaMalloc(&e->mesh_out, sizeof(float) * 9 * want));
+    e->mesh_cap = want;
+  }
+  CU(cudaMemsetAsync(e->mesh_counter, 0, sizeof(unsigned long long), e->stream));
+  launch_mesh_emit(e->S, e->selected, n_sel, e->voxel_size, e->mesh_out, (long long)e->mesh_cap, e->mesh_counter, e->stream);
+  phase_end(e, PH_GATHER, e->stream);
+  CU(cudaGetLastError());
+  e->mesh_n = (int64_t)total;
+  if (n_triangles) *n_triangles = e->mesh_n;
+  if (out && cap > 0) {
+    const size_t m = (size_t)std::min<int64_t>(cap, e->mesh_n);
+    if (m) CU(cudaMemcpyAsync(out, e->mesh_out, sizeof(float) * 9 * m, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(wait_stream(e, e->stream));
+  return TSDF_OK;
+}
+int tsdf_mesh_fetch(tsdf_handle e, float* out, int64_t cap) {
+  if (!e || !out) return fail(TSDF_E_INVALID, "null argument");
+  CU(cudaSetDevice(e->device));
+  const size_t m = (size_t)std::min<int64_t>(cap, e->mesh_n);
+  if (m) CU(cudaMemcpyAsync(out, e->mesh_out, sizeof(float) * 9 * m, cudaMemcpyDeviceToHost, e->stream));
+  CU(wait_stream(e, e->stream));
+  return TSDF_OK;
+}
+int tsdf_mesh_device_result(tsdf_handle e, const void** d_out, int64_t* n) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if (d_out) *d_out = e->mesh_out;
+  if (n) *n = e->mesh_n;
   return TSDF_OK;
 }
 

@@ -118,13 +118,21 @@ __global__ void __launch_bounds__(256) frame_allocate_kernel(DeviceState S, Fram
     }
 #pragma unroll
     for (int i = 0; i < kInlineSteps; ++i) {
-      if (lead[i]) {
-        ++n_cand;
-        if (first[i] != key[i] && !table_contains(S, key[i])) {
-          int bx, by, bz; unpack_key(key[i], bx, by, bz);
-          // Allocate() is a no-op for present blocks (voxel_hash.cu:62-77), so the (expensive) all-corners
-          // visibility test of voxel_tsdf.cu:144 runs only for absent ones
-          if (block_visible<true>(bx, by, bz, P) && table_insert(S, key[i]) == 1) ++n_new;
+      if (i < max_steps) {  // warp-uniform
+        // Allocate() is a no-op for present blocks (voxel_hash.cu:62-77), so the all-corners visibility test of
+        // voxel_tsdf.cu:144 runs only for absent ones -- and then as a warp: one corner per lane, one ballot,
+        // instead of eight serial projections on the one lane that found the block missing
+        bool absent = false;
+        if (lead[i]) { ++n_cand; absent = first[i] != key[i] && !table_contains(S, key[i]); }
+        for (unsigned todo = __ballot_sync(0xFFFFFFFFu, absent); todo; todo &= todo - 1) {
+          const int src = __ffs(todo) - 1;
+          const u64 k = __shfl_sync(0xFFFFFFFFu, key[i], src);
+          int bx, by, bz; unpack_key(k, bx, by, bz);
+          const int cx = (short)((short)(bx << 3) + ((lane >> 0) & 1) * (kBlockLen - 1));
+          const int cy = (short)((short)(by << 3) + ((lane >> 1) & 1) * (kBlockLen - 1));
+          const int cz = (short)((short)(bz << 3) + ((lane >> 2) & 1) * (kBlockLen - 1));
+          const unsigned vis = __ballot_sync(0xFFFFFFFFu, voxel_visible(cx, cy, cz, P));
+          if ((vis & 0xFFu) == 0xFFu && (int)lane == src && table_insert(S, k) == 1) ++n_new;
         }
       }
     }

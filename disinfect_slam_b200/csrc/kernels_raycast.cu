@@ -145,6 +145,12 @@ __device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int 
   return max(gx, max(gy, gz));
 }
 
+// nearest voxel of a grid position: roundf + the reference's saturating float -> short cast.  CLAMP = false is chosen on
+// the host when no sample of the view can leave (-32000, 32000) voxels (camera position + max_depth), so the
+// saturation can never act and its two integer min/max per coordinate are dropped.
+template <bool CLAMP>
+__device__ __forceinline__ int nearest_voxel(float f) { return CLAMP ? round_to_voxel(f) : __float2int_rz(roundf(f)); }
+
 template <class V>
 __device__ __forceinline__ void cache_lookup(const V& vol, const Grid& G, BlockCache& c, int px, int py, int pz) {
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
@@ -160,18 +166,18 @@ __device__ __forceinline__ float fetch_tsdf(const V& vol, const Grid& G, BlockCa
   if (!c.base) return 1.f;
   return __ldg(base_tsdf(c.base) + voxel_index(px, py, pz));
 }
-template <class V>
+template <bool CLAMP, class V>
 __device__ __forceinline__ float fetch_tsdf_f(const V& vol, const Grid& G, BlockCache& c, float3 p) {
-  return fetch_tsdf(vol, G, c, round_to_voxel(p.x), round_to_voxel(p.y), round_to_voxel(p.z));
+  return fetch_tsdf(vol, G, c, nearest_voxel<CLAMP>(p.x), nearest_voxel<CLAMP>(p.y), nearest_voxel<CLAMP>(p.z));
 }
 
 // One march sample: TSDF at the voxel nearest to p and `skip` = how many of the FOLLOWING samples are
 // guaranteed to land in unallocated space.  With d = distance of p's cell and cs voxels per cell,
 // every voxel within Chebyshev radius (d-1)*cs of p is unallocated; m further steps move the rounded
 // voxel by at most m*smax + 1 (+1 slack for float accumulation), so m = floor(((d-1)*cs - 2) / smax).
-template <class V>
+template <bool CLAMP, class V>
 __device__ __forceinline__ float march_sample(const V& vol, const Grid& G, BlockCache& c, float3 p, float inv_smax, int& skip) {
-  const int px = round_to_voxel(p.x), py = round_to_voxel(p.y), pz = round_to_voxel(p.z);
+  const int px = nearest_voxel<CLAMP>(p.x), py = nearest_voxel<CLAMP>(p.y), pz = nearest_voxel<CLAMP>(p.z);
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
   skip = 0;
   if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
@@ -192,7 +198,7 @@ __device__ __forceinline__ float march_sample(const V& vol, const Grid& G, Block
 __device__ __forceinline__ unsigned char f2u8(float f) { return (unsigned char)min(255, max(0, __float2int_rz(f))); }
 __device__ __forceinline__ float3 add3(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 
-template <bool SHARED>
+template <bool SHARED, bool CLAMP>
 __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameParams P, float step_size, SkipMap M, int row0,
                                                       int rows, uchar4* __restrict__ img_rgba, uchar4* __restrict__ img_normal,
                                                       float* __restrict__ img_depth, u64* __restrict__ packed) {
@@ -235,8 +241,14 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
 
   BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.base = nullptr;
   int skip;
-  float tsdf_prev = march_sample(vol, G, cache, pos_grid, inv_smax, skip);
-  pos_grid = add3(pos_grid, ray_step_grid);
+  float tsdf_prev = march_sample<CLAMP>(vol, G, cache, pos_grid, inv_smax, skip);
+  // x and y of the position live in one register pair for the whole march and advance in one FADD2 per step
+  // (bit-identical to two scalar adds); reading a half of the pair is free
+  f32x2 pxy = pack2(pos_grid.x, pos_grid.y);
+  const f32x2 sxy = pack2(ray_step_grid.x, ray_step_grid.y);
+  float pz = pos_grid.z;
+  const float sz = ray_step_grid.z;
+  pxy = add2(pxy, sxy); pz += sz;
   int i = 1;
 
   uint32_t out_rgba = 0u, out_normal = 0u;  // r | g << 8 | b << 16 | a << 24; a miss is (0, 0, 0, 0) like the reference
@@ -246,23 +258,29 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   for (;;) {
     if (skip > 0) {  // the next `skip` samples read +1: advance the position exactly as the reference does
       const int k = min(skip, max_step - i);
-      f32x2 pxy = pack2(pos_grid.x, pos_grid.y);  // x and y advance in one FADD2 per step
-      const f32x2 sxy = pack2(ray_step_grid.x, ray_step_grid.y);
-      float pz = pos_grid.z;
-#pragma unroll 8
-      for (int j = 0; j < k; ++j) { pxy = add2(pxy, sxy); pz += ray_step_grid.z; }
-      unpack2(pxy, pos_grid.x, pos_grid.y);
-      pos_grid.z = pz;
-      i += k;
+      if (k > 0) {
+        if (k & 1) { pxy = add2(pxy, sxy); pz += sz; }
+        if (k & 2) { pxy = add2(pxy, sxy); pz += sz; pxy = add2(pxy, sxy); pz += sz; }
+        if (k & 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { pxy = add2(pxy, sxy); pz += sz; }
+        }
+        for (int j = k >> 3; j > 0; --j) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { pxy = add2(pxy, sxy); pz += sz; }
+        }
+        i += k;
+      }
     }
     if (i >= max_step) break;
-    const float tsdf_curr = march_sample(vol, G, cache, pos_grid, inv_smax, skip);
+    const float tsdf_curr = march_sample<CLAMP>(vol, G, cache, f3(lo2(pxy), hi2(pxy), pz), inv_smax, skip);
     // ray hit front surface (voxel_tsdf.cu:260)
     if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) { hit = true; break; }
     tsdf_prev = tsdf_curr;
-    pos_grid = add3(pos_grid, ray_step_grid);
+    pxy = add2(pxy, sxy); pz += sz;
     ++i;
   }
+  pos_grid = f3(lo2(pxy), hi2(pxy), pz);
 
   // The refinement runs after the march loop so that the lanes of a warp execute it together (once per
   // warp) instead of once per distinct hit iteration.
@@ -274,11 +292,11 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
     for (;;) {
       const float3 dd = f3(pos1.x - pos2.x, pos1.y - pos2.y, pos1.z - pos2.z);
       if (!(dot3(dd, dd) >= 0.1f)) break;
-      const float tm = fetch_tsdf_f(vol, G, cache, mid);
+      const float tm = fetch_tsdf_f<CLAMP>(vol, G, cache, mid);
       if (tm < 0) pos2 = mid; else pos1 = mid;
       mid = f3((pos1.x + pos2.x) / 2.f, (pos1.y + pos2.y) / 2.f, (pos1.z + pos2.z) / 2.f);
     }
-    const int fx = round_to_voxel(mid.x), fy = round_to_voxel(mid.y), fz = round_to_voxel(mid.z);
+    const int fx = nearest_voxel<CLAMP>(mid.x), fy = nearest_voxel<CLAMP>(mid.y), fz = nearest_voxel<CLAMP>(mid.z);
     cache_lookup(vol, G, cache, fx, fy, fz);
     const unsigned char* const cbase = cache.base;
     // Block of each of the 6 neighbours first (only a neighbour across a block face needs a table lookup,
@@ -332,13 +350,22 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   }
 }
 
+// true when some sample of this view could reach +-32000 voxels, i.e. when the reference's saturating short cast could act:
+// |position| <= |camera centre| + (max_depth + one step) along the ray, in voxels, plus slack for the float accumulation
+static bool view_needs_clamp(const FrameParams& P, float step_size) {
+  const float t = fmaxf(fmaxf(fabsf(P.world_T_cam.tx), fabsf(P.world_T_cam.ty)), fabsf(P.world_T_cam.tz));
+  const float reach = (t + (P.max_depth + 2 * step_size) * 1.01f) / P.voxel_size + 64.f;
+  return !(reach < 32000.f);  // also true for NaN / inf
+}
+
 void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, const SkipMap& M, uchar4* rgba,
                     uchar4* normal, float* hit_depth, unsigned long long* packed_keys, cudaStream_t st) {
   dim3 grid((P.w + 31) / 32, (P.h + 7) / 8);
   SkipMap R = M;  // launch_build_skip_map leaves the final distances in `scratch`
   R.dist = M.scratch; R.scratch = M.dist;
   Volume<false> vol; vol.S = S;
-  raycast_kernel<false><<<grid, 256, 0, st>>>(vol, P, step_size, R, 0, P.h, rgba, normal, hit_depth, packed_keys);
+  if (view_needs_clamp(P, step_size)) raycast_kernel<false, true><<<grid, 256, 0, st>>>(vol, P, step_size, R, 0, P.h, rgba, normal, hit_depth, packed_keys);
+  else raycast_kernel<false, false><<<grid, 256, 0, st>>>(vol, P, step_size, R, 0, P.h, rgba, normal, hit_depth, packed_keys);
 }
 
 // Rows [row0, row0 + rows) of a view over a volume sharded across `n_shards` engines whose tables and pools are
@@ -352,7 +379,8 @@ void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift
   SkipMap R = M;
   R.dist = M.scratch; R.scratch = M.dist;
   Volume<true> vol; vol.shards = shards; vol.n_shards = n_shards; vol.shard_shift = shard_shift;
-  raycast_kernel<true><<<grid, 256, 0, st>>>(vol, P, step_size, R, row0, rows, rgba, normal, hit_depth, nullptr);
+  if (view_needs_clamp(P, step_size)) raycast_kernel<true, true><<<grid, 256, 0, st>>>(vol, P, step_size, R, row0, rows, rgba, normal, hit_depth, nullptr);
+  else raycast_kernel<true, false><<<grid, 256, 0, st>>>(vol, P, step_size, R, row0, rows, rgba, normal, hit_depth, nullptr);
 }
 
 }  // namespace tsdf

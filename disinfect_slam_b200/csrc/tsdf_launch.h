@@ -39,4 +39,10 @@ void launch_assign_list(const DeviceState& S, const short* points, int n, const 
                         const float* prob, cudaStream_t st);
 void launch_rehash(const DeviceState& S, int num_sms, cudaStream_t st);
 
+// kernels_mesh.cu
+void launch_mesh_count(const DeviceState& S, const int* selected, int n_selected, float voxel_size, unsigned long long* counter,
+                       cudaStream_t st);
+void launch_mesh_emit(const DeviceState& S, const int* selected, int n_selected, float voxel_size, float* out, long long cap_triangles,
+                      unsigned long long* counter, cudaStream_t st);
+
 }  // namespace tsdf

@@ -189,6 +189,21 @@ class TSDFGrid:
             check(self.L.tsdf_gather_fetch(self.h, _p(out), n.value))
         return out
 
+    def ExtractMesh(self, volumn=None, to_host=True):
+        """Triangle mesh of the zero level set from the blocks GatherVoxels(volumn) would select (all blocks if None),
+        extracted on the GPU (tsdf_extract_mesh; replaces Query + KrisLibrary meshing,
+        examples/ros_camera_driver/ros_offline.cc:258-350).  Returns float32 [n, 3, 3] (triangle, vertex, xyz), or
+        with to_host=False only the triangle count (result stays on the device: tsdf_mesh_device_result)."""
+        n = C.c_int64(0)
+        bb = None if volumn is None else np.asarray(tuple(volumn), np.float32)
+        check(self.L.tsdf_extract_mesh(self.h, _p(bb), None, 0, C.byref(n)))
+        if not to_host:
+            return n.value
+        out = np.empty((n.value, 3, 3), np.float32)
+        if n.value:
+            check(self.L.tsdf_mesh_fetch(self.h, _p(out), n.value))
+        return out
+
     def gather_device(self, bbox=None):
         """Run the selection + emit kernels only; the records stay in the engine's device buffer
         (tsdf_gather_device_result).  Returns the number of voxels selected."""

@@ -160,6 +160,20 @@ int tsdf_gather_in_bound(tsdf_handle h, const float bbox[6], float* out_xyzt, in
 int tsdf_gather_fetch(tsdf_handle h, float* out_xyzt, int64_t cap_voxels);
 int tsdf_gather_device_result(tsdf_handle h, const void** d_out_xyzt, int64_t* n_voxels);
 
+/* Triangle mesh of the zero level set, extracted on the GPU from the blocks the same bbox would select in
+ * tsdf_gather_in_bound (bbox == NULL: every block).  Replaces the reference's mesh path -- GatherVoxels' 16 B per
+ * voxel download followed by KrisLibrary's Geometry::SparseTSDFReconstruction::ExtractMesh on one CPU core
+ * (examples/ros_camera_driver/ros_offline.cc:258-318, 320-350) -- so that only the surface crosses PCIe.
+ * out_xyz = n_triangles x 3 vertices x (x, y, z) metres, voxel centres at (grid + 0.5) * voxel_size
+ * (ros_offline.cc:281-284), normals (counter-clockwise order) towards free space; triangle order unspecified.
+ * Cells with an unallocated or never-observed (weight 0) corner are not meshed.  Two-call protocol like the
+ * gathers: out_xyz == NULL only counts; the full result stays in an engine-owned device buffer until the next
+ * extraction (tsdf_mesh_fetch / tsdf_mesh_device_result). */
+int tsdf_extract_mesh(tsdf_handle h, const float* bbox /* 6 floats or NULL */, float* out_xyz, int64_t cap_triangles,
+                      int64_t* n_triangles);
+int tsdf_mesh_fetch(tsdf_handle h, float* out_xyz, int64_t cap_triangles);
+int tsdf_mesh_device_result(tsdf_handle h, const void** d_out_xyz, int64_t* n_triangles);
+
 /* VoxelHashTable::NumActiveBlock()                      utils/tsdf/voxel_hash.cu:200 */
 int tsdf_num_active_blocks(tsdf_handle h, int* n);
 int tsdf_get_counters(tsdf_handle h, tsdf_counters* out);

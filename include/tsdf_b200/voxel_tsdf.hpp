@@ -90,6 +90,16 @@ class TSDFGrid {
     return gather<Voxel>(b);
   }
 
+  // Triangles of the zero level set of the blocks GatherVoxels(volumn) would select, extracted on the GPU
+  // (tsdf_extract_mesh): 9 floats per triangle.  Replaces Query + KrisLibrary ExtractMesh (ros_offline.cc:258-318).
+  struct Triangle { float v[3][3]; };
+  std::vector<Triangle> ExtractMesh() { return mesh(nullptr); }
+  template <class Cube>
+  std::vector<Triangle> ExtractMesh(const Cube& volumn) {
+    const float b[6] = {volumn.xmin, volumn.xmax, volumn.ymin, volumn.ymax, volumn.zmin, volumn.zmax};
+    return mesh(b);
+  }
+
   int NumActiveBlock() { int n = 0; check(tsdf_num_active_blocks(h_, &n)); return n; }
   tsdf_counters Counters() { tsdf_counters c; check(tsdf_get_counters(h_, &c)); return c; }
   tsdf_handle handle() const { return h_; }
@@ -112,6 +122,14 @@ class TSDFGrid {
     check(bbox ? tsdf_gather_in_bound(h_, bbox, nullptr, 0, &n) : tsdf_gather_valid(h_, nullptr, 0, &n));
     std::vector<Voxel> ret(static_cast<size_t>(n));
     if (n) check(tsdf_gather_fetch(h_, reinterpret_cast<float*>(ret.data()), n));
+    return ret;
+  }
+  std::vector<Triangle> mesh(const float* bbox) {
+    static_assert(sizeof(Triangle) == 36, "9 floats per triangle");
+    int64_t n = 0;
+    check(tsdf_extract_mesh(h_, bbox, nullptr, 0, &n));
+    std::vector<Triangle> ret(static_cast<size_t>(n));
+    if (n) check(tsdf_mesh_fetch(h_, reinterpret_cast<float*>(ret.data()), n));
     return ret;
   }
   tsdf_handle h_ = nullptr;

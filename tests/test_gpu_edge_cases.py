@@ -58,6 +58,25 @@ def test_raycast_on_hand_built_sparse_volumes(tg, blocks):
     g.close()
 
 
+def test_raycast_at_the_edge_of_the_short_range(tg):
+    """A camera 655 m from the origin at 2 cm voxels: sample coordinates pass -32768 and the reference's float -> short
+    cast saturates (utils/tsdf/voxel_mem.cuh via .cast<short>()).  The engine picks its clamping ray-cast variant for
+    such views (the usual variant has no clamp); the images must still equal the oracle's."""
+    blocks = [[0, 0, -4096], [1, 0, -4096], [0, 1, -4096], [-1, 0, -4096], [0, -1, -4096], [0, 0, 10]]
+    g, o = slab_volume(tg, blocks)
+    K = (300.0, 300.0, 159.5, 119.5)
+    cam = tg.CameraParams(K, 240, 320)
+    ident = np.array([0, 0, 0, 1], np.float32)
+    hits = 0
+    for tz in (655.5, 655.9, 657.0):  # cam_T_world translation: the camera centre is at world z = -tz
+        t = np.array([-0.05, -0.03, tz], np.float32)
+        er = g.RayCast(4.0, cam, (ident, t))
+        orr = o.raycast(4.0, 320, 240, np.array(K, np.float32), ident, t)
+        hits += compare.compare_raycast(er, orr[:3], f"edge of range tz {tz}")["hits"]
+    assert hits > 1000
+    g.close()
+
+
 def test_rehash_in_the_middle_of_a_run(tg):
     """Fill more than half of a small table with live + tombstoned slots, then integrate: the garbage collection
     (clear + re-insert, launched when a frame retires) must leave every block reachable and the volume exactly
