@@ -552,31 +552,46 @@ def main():
     del engs
 
     # ---------------- leg 3: end to end through the host-buffer C ABI ----------------
-    e2e = None
-    if not args.no_e2e:
+    # Every step uploads each stream's frame from pinned host memory (15 B/px) and brings both rendered images and the
+    # hit depth back to pinned host memory (12 B/px), one host thread per stream (what a TSDFSystem worker is).
+    #   pipelined: tsdf_integrate_async + tsdf_raycast_async -- the copies of frame k overlap the kernels of its
+    #              neighbours; a frame's images are waited for (tsdf_raycast_wait) one frame later, all of them inside
+    #              the timed region (the `e2e` key)
+    #   sync:      tsdf_integrate + tsdf_raycast, the reference's blocking call pattern (`e2e_sync`)
+    def run_e2e(pipelined):
         engs = make_engines(blocking=oversubscribed)
-        houts = [(tsdf_grid.PinnedArray((H, Wd, 4), np.uint8), tsdf_grid.PinnedArray((H, Wd, 4), np.uint8),
-                  tsdf_grid.PinnedArray((H, Wd), np.float32)) for _ in range(B)]
+        houts = [[(tsdf_grid.PinnedArray((H, Wd, 4), np.uint8), tsdf_grid.PinnedArray((H, Wd, 4), np.uint8),
+                   tsdf_grid.PinnedArray((H, Wd), np.float32)) for _ in range(2)] for _ in range(B)]
 
-        def host_step(b, i):
+        def host_step(b, i, first):
             fi = i % n_frames
             g, p, st = engs[b], pinned[b], streams[b]
             pose = (st["q"][fi], st["t"][fi])
-            g.Integrate(p["rgb"].array[fi], p["depth"].array[fi], p["ht"].array[fi], p["lt"].array[fi], cfg.max_depth, st["K"], pose)
-            g.RayCast(cfg.max_depth, cam, pose, out=tuple(a.array for a in houts[b]))
+            out = tuple(a.array for a in houts[b][i & 1])
+            if pipelined:
+                g.Integrate(p["rgb"].array[fi], p["depth"].array[fi], p["ht"].array[fi], p["lt"].array[fi], cfg.max_depth, st["K"], pose,
+                            asynchronous=True)
+                g.RayCastAsync(cfg.max_depth, cam, pose, out)
+                if not first:
+                    g.RayCastWait()  # the previous frame's images are now in host memory
+            else:
+                g.Integrate(p["rgb"].array[fi], p["depth"].array[fi], p["ht"].array[fi], p["lt"].array[fi], cfg.max_depth, st["K"], pose)
+                g.RayCast(cfg.max_depth, cam, pose, out=out)
 
         for i in range(W):
             for b in range(B):
-                host_step(b, i)
+                host_step(b, i, i == 0)
+        for g in engs:
+            g.synchronize()
         barrier()
-        # one host thread per stream, each making the synchronous calls a TSDFSystem worker would make
         start = threading.Barrier(B + 1)
 
         def worker(b):
             torch.cuda.set_device(local_rank)
             start.wait()
             for i in range(W, W + K):
-                host_step(b, i)
+                host_step(b, i, i == W)
+            engs[b].synchronize()  # the last frame's images too
 
         ths = [threading.Thread(target=worker, args=(b,)) for b in range(B)]
         for t in ths:
@@ -593,13 +608,25 @@ def main():
             tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_s = float(tt.item())
-        e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * npx * B, "d2h_bytes_per_step": 12 * npx * B + 64 * B,
-               "api": "tsdf_integrate + tsdf_raycast (synchronous, pinned host buffers), one host thread per stream"
+        checksum = float(sum(int(houts[b][(W + K - 1) & 1][0].array[::97, ::89].sum()) for b in range(B)))
+        res = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * npx * B, "d2h_bytes_per_step": 12 * npx * B + 64 * B,
+               "api": ("tsdf_integrate_async + tsdf_raycast_async + tsdf_raycast_wait (pipelined, pinned host buffers; every frame's rgba + normal + "
+                       "hit depth reach host memory inside the timed region, waited for one frame later)" if pipelined else
+                       "tsdf_integrate + tsdf_raycast (synchronous, pinned host buffers)") + ", one host thread per stream"
                       + (", TSDF_FLAG_BLOCKING_SYNC (more waiting threads than host cores)" if oversubscribed else ""),
-               "ms_per_step": 1e3 * e2e_s / K}
+               "ms_per_step": 1e3 * e2e_s / K, "last_frame_rgba_checksum": checksum}
         for g in engs:
             g.close()
-        del engs
+        for hb in houts:
+            for pair in hb:
+                for a in pair:
+                    a.free()
+        return res
+
+    e2e = e2e_sync = None
+    if not args.no_e2e:
+        e2e_sync = run_e2e(False)
+        e2e = run_e2e(True)
     # ---------------- leg 4 (N > 1): ONE stream whose volume is sharded over all ranks ----------------
     shard = None
     if world > 1 and not args.no_sharded:
@@ -657,6 +684,7 @@ def main():
                     "mrays_per_s_kernel_only": npx * ph_n.get("raycast", 0) / (ph_ms.get("raycast", 1e-9) * 1e-3) / 1e6,
                     "note": "skip-map build + march; issue/latency bound (ncu: DRAM < 6 % of peak), not an HBM-roofline kernel"},
         "e2e": e2e,
+        "e2e_sync": e2e_sync,
         # per frame: frame_allocate, select_visible, integrate_carve + skip_fill, skip_mark, 3 x skip_pass, raycast
         "gpu_launches": 9 * B * K,
         "clocks": sampler.summary(windows[:1]),

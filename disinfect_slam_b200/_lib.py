@@ -43,6 +43,8 @@ SYMBOLS = {
     "tsdf_integrate_async": (_i32, _FRAME),
     "tsdf_integrate_device": (_i32, _FRAME + [_vp]),
     "tsdf_raycast": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsdf_raycast_async": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsdf_raycast_wait": (_i32, [_vp]),
     "tsdf_raycast_device": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsdf_raycast_resident": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "tsdf_ipc_export": (_i32, [_vp, _vp]),

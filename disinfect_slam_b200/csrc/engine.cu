@@ -60,6 +60,11 @@ struct tsdf_engine {
   void* ipc_opened[kMaxPeers][4] = {};  // pointers obtained from cudaIpcOpenMemHandle (closed at destroy)
   uint64_t volume_epoch = 1, skip_epoch = 0;
   uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
+  // pipelined RayCast (tsdf_raycast_async): two sets of output images (set 0 = the three above, set 1 allocated on first
+  // use), rendered on `stream`, copied to the host on `d2h_stream` while the next frame's kernels run
+  struct RcSet { uchar4 *rgba = nullptr, *normal = nullptr; float* depth = nullptr; cudaEvent_t rendered = nullptr, copied = nullptr; bool pending = false; } rc[2];
+  int rc_cur = 0;
+  cudaStream_t d2h_stream = nullptr;
   float4* gather_out = nullptr; size_t gather_cap = 0; int64_t gather_n = 0;
   float* mesh_out = nullptr; size_t mesh_cap = 0; int64_t mesh_n = 0;  // triangles (9 floats each), grow-only
   unsigned long long* mesh_counter = nullptr;
@@ -194,8 +199,16 @@ static int retire_slot(tsdf_engine* e, int s) {
   if ((unsigned)c[C_NONEMPTY] > (e->S.table_mask + 1) / 2) launch_rehash(e->S, e->num_sms, e->stream);
   return TSDF_OK;
 }
+// host wait for every outstanding tsdf_raycast_async copy
+static int raycast_drain(tsdf_engine* e) {
+  for (int i = 0; i < 2; ++i) {
+    if (e->rc[i].pending) { CU(cudaEventSynchronize(e->rc[i].copied)); e->rc[i].pending = false; }
+  }
+  return TSDF_OK;
+}
 static int drain(tsdf_engine* e) {
-  int rc = TSDF_OK;
+  int rc = raycast_drain(e);
+  if (rc) return rc;
   // retire in submission order so that `last` ends up describing the newest frame
   const int first = e->last_slot < 0 ? 0 : 1 - e->last_slot;
   for (int i = 0; i < 2; ++i) { const int r = retire_slot(e, (first + i) & 1); if (r != TSDF_OK) rc = r; }
@@ -303,6 +316,9 @@ int tsdf_destroy(tsdf_handle e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
+  cudaFree(e->rc[1].rgba); cudaFree(e->rc[1].normal); cudaFree(e->rc[1].depth);
+  for (int i = 0; i < 2; ++i) { if (e->rc[i].rendered) cudaEventDestroy(e->rc[i].rendered); if (e->rc[i].copied) cudaEventDestroy(e->rc[i].copied); }
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
   cudaFree(e->visible); cudaFree(e->selected); cudaFree(e->mesh_out); cudaFree(e->mesh_counter);
   cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr);
@@ -407,10 +423,50 @@ int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const floa
   return TSDF_OK;
 }
 
+int tsdf_raycast_async(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                       uint8_t* rgba, uint8_t* normal, float* hit_depth) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if ((int64_t)w * h > e->cfg.max_image_pixels) return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
+  CU(cudaSetDevice(e->device));
+  if (!e->d2h_stream) {  // first use: second image set, copy stream, events
+    const size_t npx = (size_t)e->cfg.max_image_pixels;
+    CU(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    e->rc[0].rgba = e->rgba; e->rc[0].normal = e->normal; e->rc[0].depth = e->hit_depth;
+    CU(cudaMalloc(&e->rc[1].rgba, sizeof(uchar4) * npx)); CU(cudaMalloc(&e->rc[1].normal, sizeof(uchar4) * npx)); CU(cudaMalloc(&e->rc[1].depth, sizeof(float) * npx));
+    const unsigned evf = cudaEventDisableTiming | (e->blocking_sync ? cudaEventBlockingSync : 0u);
+    for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&e->rc[i].rendered, evf)); CU(cudaEventCreateWithFlags(&e->rc[i].copied, evf)); }
+  }
+  tsdf_engine::RcSet& o = e->rc[e->rc_cur];
+  if (o.pending) { CU(cudaEventSynchronize(o.copied)); o.pending = false; }  // at most two views in flight
+  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, o.rgba, o.normal, o.depth, nullptr);
+  if (rc) return rc;
+  CU(cudaEventRecord(o.rendered, e->stream));
+  CU(cudaStreamWaitEvent(e->d2h_stream, o.rendered, 0));
+  const size_t n = (size_t)w * h;
+  if (rgba) CU(cudaMemcpyAsync(rgba, o.rgba, 4 * n, cudaMemcpyDeviceToHost, e->d2h_stream));
+  if (normal) CU(cudaMemcpyAsync(normal, o.normal, 4 * n, cudaMemcpyDeviceToHost, e->d2h_stream));
+  if (hit_depth) CU(cudaMemcpyAsync(hit_depth, o.depth, 4 * n, cudaMemcpyDeviceToHost, e->d2h_stream));
+  CU(cudaEventRecord(o.copied, e->d2h_stream));
+  o.pending = true;  // the host waits for this copy before the set is rendered into again (two calls from now)
+  e->rc_cur ^= 1;
+  return TSDF_OK;
+}
+int tsdf_raycast_wait(tsdf_handle e) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  // oldest outstanding view first: after the flip rc_cur names the set used two calls ago
+  for (int k = 0; k < 2; ++k) {
+    tsdf_engine::RcSet& o = e->rc[(e->rc_cur + k) & 1];
+    if (o.pending) { CU(cudaEventSynchronize(o.copied)); o.pending = false; return TSDF_OK; }
+  }
+  return TSDF_OK;
+}
+
 int tsdf_raycast(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
                  uint8_t* rgba, uint8_t* normal, float* hit_depth) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
   if ((int64_t)w * h > e->cfg.max_image_pixels) return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
+  { int rcd = raycast_drain(e); if (rcd) return rcd; }
   int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, e->rgba, e->normal, e->hit_depth, nullptr);
   if (rc) return rc;
   const size_t n = (size_t)w * h;
@@ -425,7 +481,9 @@ int tsdf_raycast_resident(tsdf_handle e, float max_depth, int w, int h, const fl
                           const void** d_rgba, const void** d_normal, const void** d_hit_depth) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
   if ((int64_t)w * h > e->cfg.max_image_pixels) return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
-  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, e->rgba, e->normal, e->hit_depth, nullptr);
+  int rc = raycast_drain(e);
+  if (rc) return rc;
+  rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, e->rgba, e->normal, e->hit_depth, nullptr);
   if (rc) return rc;
   if (d_rgba) *d_rgba = e->rgba;
   if (d_normal) *d_normal = e->normal;

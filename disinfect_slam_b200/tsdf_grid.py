@@ -149,6 +149,22 @@ class TSDFGrid:
         check(self.L.tsdf_raycast(self.h, max_depth, w, h, _p(K), _p(q), _p(t), _p(rgba), _p(normal), _p(depth)))
         return rgba, normal, depth
 
+    def RayCastAsync(self, max_depth, virtual_cam, cam_T_world, out):
+        """Pipelined RayCast (tsdf_raycast_async): `out` = (rgba, normal, depth) pinned host arrays (PinnedArray views), valid
+        after RayCastWait() / synchronize(); at most two views in flight."""
+        K = _f32(virtual_cam.intrinsics, 4)
+        h, w = int(virtual_cam.img_h), int(virtual_cam.img_w)
+        q, t = _pose(cam_T_world)
+        rgba, normal, depth = out
+        for a, shp, dt in ((rgba, (h, w, 4), np.uint8), (normal, (h, w, 4), np.uint8), (depth, (h, w), np.float32)):
+            if a is not None and (a.shape != shp or a.dtype != dt or not a.flags["C_CONTIGUOUS"]):
+                raise ValueError("RayCastAsync out buffers must be contiguous rgba/normal uint8 HxWx4, depth float32 HxW")
+        check(self.L.tsdf_raycast_async(self.h, max_depth, w, h, _p(K), _p(q), _p(t), _p(rgba), _p(normal), _p(depth)))
+
+    def RayCastWait(self):
+        """Blocks until the images of the oldest outstanding RayCastAsync are in host memory."""
+        check(self.L.tsdf_raycast_wait(self.h))
+
     def RayCastDevice(self, max_depth, virtual_cam, cam_T_world, d_rgba=None, d_normal=None, d_depth=None,
                       d_packed=None):
         K = _f32(virtual_cam.intrinsics, 4)

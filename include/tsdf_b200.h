@@ -114,6 +114,14 @@ int tsdf_integrate_device(tsdf_handle h, const void* d_rgb, const void* d_depth,
 int tsdf_raycast(tsdf_handle h, float max_depth, int width, int height, const float K[4], const float q_xyzw[4],
                  const float t_xyz[3], uint8_t* rgba /* HxWx4 */, uint8_t* normal /* HxWx4 */,
                  float* hit_depth /* HxW */);
+/* Pipelined variant: enqueues the render and the device->host copies (on their own stream, from one of two engine-owned
+ * image sets) and returns; a following tsdf_integrate_async overlaps the copies.  tsdf_raycast_wait() blocks until the
+ * images of the OLDEST outstanding call are in host memory; at most two calls are outstanding (a third waits for the
+ * first).  The host buffers should be pinned (tsdf_host_alloc) and must stay untouched until waited for.
+ * tsdf_synchronize() and every synchronous call wait for all of them. */
+int tsdf_raycast_async(tsdf_handle h, float max_depth, int width, int height, const float K[4], const float q_xyzw[4],
+                       const float t_xyz[3], uint8_t* rgba, uint8_t* normal, float* hit_depth);
+int tsdf_raycast_wait(tsdf_handle h);
 /* Device-output variant: results stay on the GPU (replacement for GLImage8UC4::LoadCuda,
  * utils/gl/image.cc:108-119).  Pointers are device memory, each optional; if `packed_min_keys`
  * is non-NULL it receives per ray two uint64 = (float_bits(hit_depth) << 32) | rgba / normal, the
@@ -163,7 +171,9 @@ int tsdf_gather_device_result(tsdf_handle h, const void** d_out_xyzt, int64_t* n
 /* Triangle mesh of the zero level set, extracted on the GPU from the blocks the same bbox would select in
  * tsdf_gather_in_bound (bbox == NULL: every block).  Replaces the reference's mesh path -- GatherVoxels' 16 B per
  * voxel download followed by KrisLibrary's Geometry::SparseTSDFReconstruction::ExtractMesh on one CPU core
- * (examples/ros_camera_driver/ros_offline.cc:258-318, 320-350) -- so that only the surface crosses PCIe.
+ * (examples/ros_camera_driver/ros_offline.cc:258-318, 320-350): the meshing itself moves to the GPU (the triangle
+ * soup of a full-resolution surface is about as large as the voxels it came from; keep it on the device with
+ * tsdf_mesh_device_result when the consumer is on the GPU).
  * out_xyz = n_triangles x 3 vertices x (x, y, z) metres, voxel centres at (grid + 0.5) * voxel_size
  * (ros_offline.cc:281-284), normals (counter-clockwise order) towards free space; triangle order unspecified.
  * Cells with an unallocated or never-observed (weight 0) corner are not meshed.  Two-call protocol like the

@@ -221,3 +221,38 @@ def test_device_input_path_and_sharding(grid_mod):
     assert np.array_equal(np.concatenate([p[2] for p in parts])[order], fc)
     for g in [full] + shards:
         g.close()
+
+
+def test_pipelined_raycast_matches_the_synchronous_call(tsdf_lib):
+    """tsdf_integrate_async + tsdf_raycast_async + tsdf_raycast_wait (two views in flight, copies on their own stream)
+    deliver exactly the images of the blocking tsdf_integrate + tsdf_raycast sequence."""
+    from disinfect_slam_b200 import tsdf_grid
+    cfg = synth.config("tiny")
+    sc = synth.Scene(cfg)
+    cam = tsdf_grid.CameraParams(sc.frame(0)["K"], cfg.height, cfg.width)
+    mk = lambda: tsdf_grid.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots)  # noqa: E731
+    a, b = mk(), mk()
+    n = 6
+    bufs = [tuple(tsdf_grid.PinnedArray(s, d) for s, d in (((cfg.height, cfg.width, 4), np.uint8), ((cfg.height, cfg.width, 4), np.uint8),
+                                                            ((cfg.height, cfg.width), np.float32))) for _ in range(2)]
+    want, got = [], []
+    for i in range(n):
+        f = sc.frame(i)
+        a.Integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], (f["q"], f["t"]))
+        want.append([x.copy() for x in a.RayCast(cfg.max_depth, cam, (f["q"], f["t"]))])
+    for i in range(n):
+        f = sc.frame(i)
+        b.Integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], (f["q"], f["t"]), asynchronous=True)
+        b.RayCastAsync(cfg.max_depth, cam, (f["q"], f["t"]), tuple(x.array for x in bufs[i & 1]))
+        if i > 0:
+            b.RayCastWait()  # frame i - 1 is complete, frame i may still be in flight
+            got.append([x.array.copy() for x in bufs[(i - 1) & 1]])
+    b.synchronize()
+    got.append([x.array.copy() for x in bufs[(n - 1) & 1]])
+    for i in range(n):
+        for w, g in zip(want[i], got[i]):
+            assert np.array_equal(w.view(np.uint8), g.view(np.uint8)), i
+    # a blocking call after pipelined ones sees a quiescent engine
+    f = sc.frame(n)
+    assert np.array_equal(b.RayCast(cfg.max_depth, cam, (f["q"], f["t"]))[0], a.RayCast(cfg.max_depth, cam, (f["q"], f["t"]))[0])
+    a.close(); b.close()
