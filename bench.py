@@ -661,7 +661,7 @@ def main():
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed ncu capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("integrate_carve_kernel", {}).get("dram_bytes_per_launch")
+        traffic = next((v.get("dram_bytes_per_launch") for k, v in tj.items() if "integrate_carve_kernel" in k and isinstance(v, dict)), None)
     except Exception:
         tj = {}
     line = {

@@ -22,7 +22,7 @@ namespace tsdf {
 //      8-corner visibility test and the CAS insert.
 // ------------------------------------------------------------------------------------------
 constexpr int kInlineSteps = 4;
-__global__ void __launch_bounds__(256) frame_allocate_kernel(DeviceState S, FrameParams P,
+__global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, FrameParams P,
                                                              const unsigned char* __restrict__ rgb,
                                                              const float* __restrict__ depth,
                                                              const float* __restrict__ ht,

@@ -55,7 +55,7 @@ def config(name):
     c2h = SceneConfig("config2_l515_640x360_5mm", 640, 360, L515_HALF_K, 0.005, 0.03, 4.0, 100, depth_factor=4000.0,
                       pool_blocks=1 << 20, table_slots=1 << 23)
     c3 = SceneConfig("config3_room_1280x720_2cm", 1280, 720, k2, 0.02, 0.12, 4.0, 200, room_half=(8.0, 3.0, 8.0),
-                     depth_factor=4000.0, traj_radius=5.0, n_objects=24)
+                     depth_factor=4000.0, traj_radius=5.0, n_objects=24, extra={"look": "out"})
     c4 = SceneConfig("config4_raycast_1920x1080", 1920, 1080, (1400.0, 1400.0, 959.5, 539.5), 0.01, 0.06, 4.0, 32)
     tiny = SceneConfig("tiny_160x120_2cm", 160, 120, tuple(v * 0.25 for v in TUM_K), 0.02, 0.12, 4.0, 12,
                        pool_blocks=1 << 15, table_slots=1 << 18)
@@ -104,6 +104,10 @@ class Scene:
         c = np.array([r * np.cos(a), 0.15 * np.sin(2 * a), r * np.sin(a)])
         # look across the room centre towards the far wall, with a slow pitch oscillation
         target = np.array([-1.5 * r * np.cos(a + 0.3), -0.3 + 0.25 * np.sin(3 * a), -1.5 * r * np.sin(a + 0.3)])
+        if cfg.extra.get("look") == "out":
+            # halls much larger than max_depth: face the NEAR wall instead (slightly ahead of the direction of travel),
+            # so that a lap sweeps every wall within range
+            target = np.array([3.0 * r * np.cos(a + 0.25), -0.2 + 1.2 * np.sin(3 * a), 3.0 * r * np.sin(a + 0.25)])
         f = target - c
         f /= np.linalg.norm(f)
         up = np.array([0.0, 1.0, 0.0])

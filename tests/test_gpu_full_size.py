@@ -2,7 +2,9 @@
 few seconds; here a few frames of each named config run through both):
   config 1  640x480 TUM intrinsics, 1 cm voxels: Integrate + GatherValid
   config 2  1280x720 L515/ZED-style, 5 mm voxels: Integrate + RayCast from the same camera
+  config 3  room-scale hall, 2 cm voxels, 1280x720: Integrate + bounded GatherVoxels + mesh of the same box
   config 4  1920x1080 virtual views over a pre-built volume
+  config 5  (per-stream part) GatherVoxels with the +-8 m query box of the reference's ROS node
 plus size-independent properties on a longer run: counters add up, re-integrating is deterministic, a gather of
 the whole volume equals the block export."""
 import numpy as np
@@ -55,6 +57,21 @@ def test_config2_integrate_and_raycast(tg):
     rep = compare.compare_raycast(g.RayCast(cfg.max_depth, cam, (f["q"], f["t"])),
                                   o.raycast(cfg.max_depth, cfg.width, cfg.height, f["K"], f["q"], f["t"])[:3], "config2 RayCast")
     assert rep["hits"] > 0.9 * rep["rays"]
+    g.close()
+
+
+def test_config3_room_scale_integrate_bounded_gather_and_mesh(tg):
+    from oracle import mesh_oracle
+    cfg = synth.config("config3")
+    sc, g, o, f = run(tg, cfg, (0, 40, 80))  # three views far apart on the 5 m trajectory of the 16 x 6 x 16 m hall
+    assert compare.compare_volumes(g.export(), o.export(), "config3")["tsdf_bit_exact"]
+    bbox = (-8.0, 0.0, -3.0, 3.0, -8.0, 8.0)  # half of the hall
+    rep = compare.compare_gather(g.GatherVoxels(tg.BoundingCube(*bbox)), o.gather(bbox), "config3 GatherVoxels")
+    assert rep["tsdf_bit_exact"] and 0 < rep["n_voxels"] < g.NumActiveBlock() * 512
+    keys, tsdf, rgbw, _ = o.export()
+    got, want = g.ExtractMesh(bbox), mesh_oracle.extract_mesh(keys, tsdf, rgbw, cfg.voxel_size, bbox)
+    assert got.shape == want.shape and len(got) > 10000
+    assert np.array_equal(mesh_oracle.canonical_triangles(got).view(np.uint32), mesh_oracle.canonical_triangles(want).view(np.uint32))
     g.close()
 
 
