@@ -627,6 +627,33 @@ def main():
     if not args.no_e2e:
         e2e_sync = run_e2e(False)
         e2e = run_e2e(True)
+        # what the e2e number runs against: the host <-> device copy bandwidth of this box, pinned memory, both directions
+        # busy at once (256 MB each, best of 5) -- the e2e leg moves 15 B/px in and 12 B/px out per frame
+        try:
+            nb = 256 << 20
+            hp_in, hp_out = torch.empty(nb, dtype=torch.uint8, pin_memory=True), torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            d_in, d_out = torch.empty(nb, dtype=torch.uint8, device=dev), torch.empty(nb, dtype=torch.uint8, device=dev)
+            s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            best = {"h2d": 0.0, "d2h": 0.0, "both": 0.0}
+            for mode in ("h2d", "d2h", "both"):
+                for rep in range(5):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    if mode in ("h2d", "both"):
+                        with torch.cuda.stream(s1):
+                            d_in.copy_(hp_in, non_blocking=True)
+                    if mode in ("d2h", "both"):
+                        with torch.cuda.stream(s2):
+                            hp_out.copy_(d_out, non_blocking=True)
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    best[mode] = max(best[mode], nb / dt / 1e9)
+            e2e["pcie_measured_gbs"] = {"h2d_alone": best["h2d"], "d2h_alone": best["d2h"], "each_direction_when_both_run": best["both"]}
+            e2e["h2d_gbs_in_e2e"] = e2e["value"] / world * 15 * npx / 1e9
+            e2e["d2h_gbs_in_e2e"] = e2e["value"] / world * 12 * npx / 1e9
+            del hp_in, hp_out, d_in, d_out
+        except Exception as ex:  # supplementary only
+            e2e["pcie_measured_gbs"] = {"error": repr(ex)}
     # ---------------- leg 4 (N > 1): ONE stream whose volume is sharded over all ranks ----------------
     shard = None
     if world > 1 and not args.no_sharded:
