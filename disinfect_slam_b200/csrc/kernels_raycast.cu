@@ -134,10 +134,17 @@ __device__ __forceinline__ const float* base_logit(const unsigned char* b) { ret
 
 // Chebyshev distance (cells) from block (bx,by,bz) to the nearest cell holding an active block;
 // 0 = this cell holds one (the block itself may still be absent when shift > 0)
-__device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int bz) {
+// `leaving`: bit a = the ray does not increase along axis a, bit 3 + a = it does not decrease.  A sample outside the
+// AABB on a side the ray is moving away from (or along) can never be followed by a sample inside it -- the accumulated
+// position is monotonic per axis and no block exists outside the AABB -- so the ray is a miss: kEscaped is returned.
+constexpr int kEscaped = 1 << 30;
+__device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int bz, unsigned leaving = 0u) {
   const int cx = (bx - G.ox) >> G.shift, cy = (by - G.oy) >> G.shift, cz = (bz - G.oz) >> G.shift;
   if ((unsigned)cx < (unsigned)G.nx && (unsigned)cy < (unsigned)G.ny && (unsigned)cz < (unsigned)G.nz)
     return __ldg(G.dist + ((cz * G.ny + cy) * G.nx + cx));  // at most 2^22 cells
+  const unsigned below = (cx < 0 ? 1u : 0u) | (cy < 0 ? 2u : 0u) | (cz < 0 ? 4u : 0u);
+  const unsigned above = (cx >= G.nx ? 8u : 0u) | (cy >= G.ny ? 16u : 0u) | (cz >= G.nz ? 32u : 0u);
+  if ((below | above) & leaving) return kEscaped;
   // outside the AABB: the gap to the box (in cells) is a lower bound of the distance
   const int gx = cx < 0 ? -cx : (cx >= G.nx ? cx - G.nx + 1 : 0);
   const int gy = cy < 0 ? -cy : (cy >= G.ny ? cy - G.ny + 1 : 0);
@@ -176,18 +183,20 @@ __device__ __forceinline__ float fetch_tsdf_f(const V& vol, const Grid& G, Block
 // every voxel within Chebyshev radius (d-1)*cs of p is unallocated; m further steps move the rounded
 // voxel by at most m*smax + 1 (+1 slack for float accumulation), so m = floor(((d-1)*cs - 2) / smax).
 template <bool CLAMP, class V>
-__device__ __forceinline__ float march_sample(const V& vol, const Grid& G, BlockCache& c, float3 p, float inv_smax, int& skip) {
+__device__ __forceinline__ float march_sample(const V& vol, const Grid& G, BlockCache& c, float3 p, float inv_smax, unsigned leaving,
+                                              int& skip) {
   const int px = nearest_voxel<CLAMP>(p.x), py = nearest_voxel<CLAMP>(p.y), pz = nearest_voxel<CLAMP>(p.z);
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
   skip = 0;
   if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
     c.bx = bx; c.by = by; c.bz = bz;
-    const int d = cell_distance(G, bx, by, bz);
+    const int d = cell_distance(G, bx, by, bz, leaving);
     if (d == 0) {
       c.base = vol.find(bx, by, bz);
     } else {
       c.base = nullptr;
-      if (d >= 2) skip = __float2int_rd((float)(((d - 1) << (3 + G.shift)) - 2) * inv_smax);
+      if (d == kEscaped) skip = kEscaped;  // the ray has left the volume for good
+      else if (d >= 2) skip = __float2int_rd((float)(((d - 1) << (3 + G.shift)) - 2) * inv_smax);
       return 1.f;
     }
   }
@@ -241,7 +250,10 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
 
   BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.base = nullptr;
   int skip;
-  float tsdf_prev = march_sample<CLAMP>(vol, G, cache, pos_grid, inv_smax, skip);
+  // sides of the block AABB this ray can only move away from (see cell_distance)
+  const unsigned leaving = (ray_step_grid.x <= 0.f ? 1u : 0u) | (ray_step_grid.y <= 0.f ? 2u : 0u) | (ray_step_grid.z <= 0.f ? 4u : 0u) |
+                           (ray_step_grid.x >= 0.f ? 8u : 0u) | (ray_step_grid.y >= 0.f ? 16u : 0u) | (ray_step_grid.z >= 0.f ? 32u : 0u);
+  float tsdf_prev = march_sample<CLAMP>(vol, G, cache, pos_grid, inv_smax, leaving, skip);
   // x and y of the position live in one register pair for the whole march and advance in one FADD2 per step
   // (bit-identical to two scalar adds); reading a half of the pair is free
   f32x2 pxy = pack2(pos_grid.x, pos_grid.y);
@@ -257,6 +269,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   bool hit = false;
   for (;;) {
     if (skip > 0) {  // the next `skip` samples read +1: advance the position exactly as the reference does
+      if (skip == kEscaped) break;  // ... all of them: a miss, whose position nobody reads
       const int k = min(skip, max_step - i);
       if (k > 0) {
         if (k & 1) { pxy = add2(pxy, sxy); pz += sz; }
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
       }
     }
     if (i >= max_step) break;
-    const float tsdf_curr = march_sample<CLAMP>(vol, G, cache, f3(lo2(pxy), hi2(pxy), pz), inv_smax, skip);
+    const float tsdf_curr = march_sample<CLAMP>(vol, G, cache, f3(lo2(pxy), hi2(pxy), pz), inv_smax, leaving, skip);
     // ray hit front surface (voxel_tsdf.cu:260)
     if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) { hit = true; break; }
     tsdf_prev = tsdf_curr;
