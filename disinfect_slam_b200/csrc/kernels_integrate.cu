@@ -203,9 +203,10 @@ __global__ void __launch_bounds__(256) select_visible_kernel(DeviceState S, Fram
 // integrate_carve_kernel: persistent warps over a device-side queue of WORK ITEMS = (visible block, group of
 // SLABS 128-voxel slabs).  A lane owns 4 consecutive-x voxels of a slab, so every voxel-plane access is one 16-byte
 // LDG/STG and the warp covers 512 contiguous bytes per plane.  A slab's three planes are requested before its
-// projection arithmetic, its 4 pixel gathers are issued together, and the next item's directory entry is fetched
-// one item ahead.  Items finer than a block keep the tail short (a frame has only ~2.5 visible blocks per resident
-// warp); the first item of every warp is assigned statically (no start-up burst on the queue counter).
+// projection arithmetic, its pixel gathers are issued pair by pair (the second pair's projection covers the first
+// pair's latency), and the next item's directory entry is fetched one item ahead.  The first item of every warp is
+// assigned statically (no start-up burst on the queue counter).  SLABS = 4 (whole blocks) is what runs: with only
+// ~2.5 visible blocks per resident warp finer items would shorten the tail, but measured slower (see the launcher).
 //   per voxel: voxel_tsdf.cu:157-203 (projection, nearest pixel, SDF, truncation, weighted running averages,
 //   weight clamp); per block: voxel_tsdf.cu:214-229 (min |tsdf| >= .9 -> free): every item adds
 //   1 + 256 * [its voxels are all >= .9] to the block's word of `vis_state`; the item that completes the block
