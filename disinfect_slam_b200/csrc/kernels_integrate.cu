@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kerne
     uint32_t* const base_rgbw = block_rgbw(S, idx) + lane * 4;
     float* const base_logit = block_logit(S, idx) + lane * 4;
 
-    float item_min = 2.f;
+    float item_min = __int_as_float(0x7FFFFFFF);  // NaN: fminf's identity; a block of nothing but NaN voxels is not carved (NaN >= .9 is false), like the reference
     const int gy = (short)((by << 3) + vy);
     const int gx0 = (bx << 3) + vx0;
     const float wy = (float)gy * P.voxel_size;

@@ -77,6 +77,35 @@ def test_raycast_at_the_edge_of_the_short_range(tg):
     g.close()
 
 
+def test_integrate_with_divisors_outside_the_shared_reciprocal_range(tg):
+    """max_depth >= 2^20 (or a truncation / weight outside (2^-20, 2^20)) switches Integrate to its true-division kernel
+    variant; a depth equal to max_depth on a fresh voxel gives weight 0 -> 0 / 0 like the reference (cold fallback of
+    the usual variant).  Both must equal the oracle bit for bit."""
+    cfg = synth.config("tiny")
+    sc = synth.Scene(cfg)
+    for max_depth, poison in ((2.0e6, False), (cfg.max_depth, True)):
+        g = tg.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots)
+        o = Oracle(cfg.voxel_size, cfg.truncation)
+        for i in range(3):
+            f = sc.frame(i)
+            depth = f["depth"].copy()
+            if poison:  # some pixels exactly at max_depth: weight_new == 0, combined weight 0 on never-seen voxels
+                depth[::7, ::5] = np.where(depth[::7, ::5] > 0, np.float32(max_depth), 0)
+            oc = o.integrate(f["rgb"], depth, f["ht"], f["lt"], max_depth, f["K"], f["q"], f["t"])
+            g.Integrate(f["rgb"], depth, f["ht"], f["lt"], max_depth, f["K"], (f["q"], f["t"]))
+            ec = g.counters()
+            assert (ec["n_new"], ec["n_visible"], ec["n_updated"], ec["n_carved"]) == (oc["n_new"], oc["n_vis"], oc["n_upd"], oc["n_carved"]), (max_depth, i)
+        ek, et, er, ep = g.export()
+        ok, ot, orr, op = o.export()
+        assert np.array_equal(ek, ok)
+        nan = np.isnan(ot)
+        assert nan.any() == poison and np.array_equal(np.isnan(et), nan), max_depth   # 0 / 0 voxels: NaN in both (payloads are platform-specific)
+        assert np.array_equal(et[~nan].view(np.uint32), ot[~nan].view(np.uint32)), max_depth
+        assert np.array_equal(er, orr) and np.array_equal(np.isnan(ep), np.isnan(op))
+        assert np.abs(ep[~np.isnan(op)] - op[~np.isnan(op)]).max() <= 1e-5
+        g.close()
+
+
 def test_rehash_in_the_middle_of_a_run(tg):
     """Fill more than half of a small table with live + tombstoned slots, then integrate: the garbage collection
     (clear + re-insert, launched when a frame retires) must leave every block reachable and the volume exactly
