@@ -53,6 +53,11 @@ __global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restri
   const uint4 cap16 = make_uint4(0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 15) / 16; i += gridDim.x * blockDim.x)
     reinterpret_cast<uint4*>(M.dist)[i] = cap16;
+  if (shift == 0 && n_shards == 1) {  // one cell = one block of one engine: a dense block index beside the distances
+    const int4 none = make_int4(-1, -1, -1, -1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 3) / 4; i += gridDim.x * blockDim.x)
+      reinterpret_cast<int4*>(M.index)[i] = none;
+  }
 }
 
 __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M) {
@@ -65,7 +70,9 @@ __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restri
       if (k == kEmpty) continue;
       int bx, by, bz; unpack_key(k, bx, by, bz);
       const int cx = (bx - ox) >> shift, cy = (by - oy) >> shift, cz = (bz - oz) >> shift;
-      M.dist[((size_t)cz * ny + cy) * nx + cx] = 0;
+      const size_t cell = ((size_t)cz * ny + cy) * nx + cx;
+      M.dist[cell] = 0;
+      if (shift == 0 && n_shards == 1) M.index[cell] = i;  // directory position = pool index
     }
   }
 }
@@ -106,21 +113,25 @@ void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& 
 // ------------------------------------------------------------------------------------------
 // ray march
 // ------------------------------------------------------------------------------------------
-struct Grid { int ox, oy, oz, nx, ny, nz, shift; const unsigned char* dist; };
+struct Grid { int ox, oy, oz, nx, ny, nz, shift; const unsigned char* dist; const int* index; };
 struct BlockCache { int bx, by, bz; const unsigned char* base; };  // bx = INT_MIN: nothing cached; base = null: absent
 
 // Where the voxels of a block live.  Local: this engine's table and pool.  Shared: the table and pool of the shard
 // that owns the block coordinate (owner_of), reached through peer-mapped pointers -- NVLink loads inside the march.
 template <bool SHARED> struct Volume;
 template <> struct Volume<false> {
+  static constexpr bool kDenseIndex = true;
   DeviceState S;
+  __device__ __forceinline__ const unsigned char* at(int idx) const { return idx < 0 ? nullptr : S.voxels + (size_t)idx * kBlockBytes; }
   __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
     const int idx = table_find(S, pack_key(bx, by, bz));
     return idx < 0 ? nullptr : S.voxels + (size_t)idx * kBlockBytes;
   }
 };
 template <> struct Volume<true> {
+  static constexpr bool kDenseIndex = false;
   const PeerView* shards; int n_shards, shard_shift;
+  __device__ __forceinline__ const unsigned char* at(int) const { return nullptr; }
   __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
     const u64 key = pack_key(bx, by, bz);
     const PeerView& v = shards[owner_of(key, n_shards, shard_shift)];
@@ -138,10 +149,12 @@ __device__ __forceinline__ const float* base_logit(const unsigned char* b) { ret
 // AABB on a side the ray is moving away from (or along) can never be followed by a sample inside it -- the accumulated
 // position is monotonic per axis and no block exists outside the AABB -- so the ray is a miss: kEscaped is returned.
 constexpr int kEscaped = 1 << 30;
-__device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int bz, unsigned leaving = 0u) {
+__device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int bz, int& cell, unsigned leaving = 0u) {
   const int cx = (bx - G.ox) >> G.shift, cy = (by - G.oy) >> G.shift, cz = (bz - G.oz) >> G.shift;
-  if ((unsigned)cx < (unsigned)G.nx && (unsigned)cy < (unsigned)G.ny && (unsigned)cz < (unsigned)G.nz)
-    return __ldg(G.dist + ((cz * G.ny + cy) * G.nx + cx));  // at most 2^22 cells
+  if ((unsigned)cx < (unsigned)G.nx && (unsigned)cy < (unsigned)G.ny && (unsigned)cz < (unsigned)G.nz) {
+    cell = (cz * G.ny + cy) * G.nx + cx;  // at most 2^22 cells
+    return __ldg(G.dist + cell);
+  }
   const unsigned below = (cx < 0 ? 1u : 0u) | (cy < 0 ? 2u : 0u) | (cz < 0 ? 4u : 0u);
   const unsigned above = (cx >= G.nx ? 8u : 0u) | (cy >= G.ny ? 16u : 0u) | (cz >= G.nz ? 32u : 0u);
   if ((below | above) & leaving) return kEscaped;
@@ -158,12 +171,25 @@ __device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int 
 template <bool CLAMP>
 __device__ __forceinline__ int nearest_voxel(float f) { return CLAMP ? round_to_voxel(f) : __float2int_rz(roundf(f)); }
 
+// voxels of block (bx, by, bz), whose cell holds an active block (distance 0): straight from the dense index when one cell
+// is one block of this engine (the usual case), through the owner's hash table otherwise
+template <class V>
+__device__ __forceinline__ const unsigned char* block_in_cell(const V& vol, const Grid& G, int cell, int bx, int by, int bz) {
+  if (V::kDenseIndex && G.shift == 0) return vol.at(__ldg(G.index + cell));
+  return vol.find(bx, by, bz);
+}
+template <class V>
+__device__ __forceinline__ const unsigned char* block_or_null(const V& vol, const Grid& G, int bx, int by, int bz) {
+  int cell = 0;
+  return cell_distance(G, bx, by, bz, cell) == 0 ? block_in_cell(vol, G, cell, bx, by, bz) : nullptr;
+}
+
 template <class V>
 __device__ __forceinline__ void cache_lookup(const V& vol, const Grid& G, BlockCache& c, int px, int py, int pz) {
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
   if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
     c.bx = bx; c.by = by; c.bz = bz;
-    c.base = cell_distance(G, bx, by, bz) == 0 ? vol.find(bx, by, bz) : nullptr;
+    c.base = block_or_null(vol, G, bx, by, bz);
   }
 }
 // Retrieve<VoxelTSDF>: absent -> VoxelTSDF() == +1 (voxel_types.cu:8)
@@ -190,9 +216,10 @@ __device__ __forceinline__ float march_sample(const V& vol, const Grid& G, Block
   skip = 0;
   if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
     c.bx = bx; c.by = by; c.bz = bz;
-    const int d = cell_distance(G, bx, by, bz, leaving);
+    int cell = 0;
+    const int d = cell_distance(G, bx, by, bz, cell, leaving);
     if (d == 0) {
-      c.base = vol.find(bx, by, bz);
+      c.base = block_in_cell(vol, G, cell, bx, by, bz);
     } else {
       c.base = nullptr;
       if (d == kEscaped) skip = kEscaped;  // the ray has left the volume for good
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   const int idx = y * P.w + x;
   Grid G;
   G.ox = M.hdr[0]; G.oy = M.hdr[1]; G.oz = M.hdr[2]; G.nx = M.hdr[3]; G.ny = M.hdr[4]; G.nz = M.hdr[5]; G.shift = M.hdr[6];
-  G.dist = M.dist;
+  G.dist = M.dist; G.index = M.index;
 
   // voxel_tsdf.cu:243-250
   const float3 pos_cam = kmul(P.Kinv, f3((float)x, (float)y, 1.f));
@@ -324,7 +351,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
       nbase[n] = cbase;
       if (((nx[n] ^ fx) | (ny[n] ^ fy) | (nz[n] ^ fz)) >> 3) {  // different block coordinate
         const int bx = nx[n] >> 3, by = ny[n] >> 3, bz = nz[n] >> 3;
-        nbase[n] = cell_distance(G, bx, by, bz) == 0 ? vol.find(bx, by, bz) : nullptr;
+        nbase[n] = block_or_null(vol, G, bx, by, bz);
       }
     }
     uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
