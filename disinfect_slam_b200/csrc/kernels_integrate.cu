@@ -10,6 +10,8 @@
 #include "tsdf_device.cuh"
 #include "tsdf_launch.h"
 
+#include <atomic>
+
 namespace tsdf {
 
 // ------------------------------------------------------------------------------------------
@@ -456,10 +458,14 @@ static bool div_safe_host(float b) { return b > 9.5367431640625e-07f && b < 1048
 template <int SLABS, bool FAST>
 static void launch_integrate_variant(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
                                      int num_sms, cudaStream_t st) {
-  static int ctas_per_sm = 0;  // persistent warps: exactly the resident CTAs, work comes from the device-side queue
+  // persistent warps: exactly the resident CTAs, work comes from the device-side queue (engines on several host threads
+  // may race to fill this in: they all compute the same value)
+  static std::atomic<int> cached{0};
+  int ctas_per_sm = cached.load(std::memory_order_relaxed);
   if (ctas_per_sm == 0) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, integrate_carve_kernel<SLABS, FAST>, 256, 0) != cudaSuccess || ctas_per_sm < 1)
       ctas_per_sm = 2;
+    cached.store(ctas_per_sm, std::memory_order_relaxed);
   }
   integrate_carve_kernel<SLABS, FAST><<<num_sms * ctas_per_sm, 256, 0, st>>>(S, P, visible, vis_state, tex, .9f);
 }
