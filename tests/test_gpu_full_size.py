@@ -75,6 +75,23 @@ def test_config3_room_scale_integrate_bounded_gather_and_mesh(tg):
     g.close()
 
 
+def test_integrate_at_the_maximum_image_size(tg):
+    """1920 x 1080 is the largest frame the reference accepts (MAX_IMG_SIZE, voxel_tsdf.cu:10-12): one such frame through
+    Integrate + RayCast equals the oracle; one pixel more is refused with TSDF_E_INVALID instead of overrunning."""
+    cfg = synth.config("config2").scaled(1.5, "config2_1920x1080")
+    assert (cfg.width, cfg.height) == (1920, 1080)
+    sc, g, o, f = run(tg, cfg, (0,))
+    assert compare.compare_volumes(g.export(), o.export(), "1080p")["tsdf_bit_exact"]
+    cam = tg.CameraParams(f["K"], cfg.height, cfg.width)
+    rep = compare.compare_raycast(g.RayCast(cfg.max_depth, cam, (f["q"], f["t"])),
+                                  o.raycast(cfg.max_depth, cfg.width, cfg.height, f["K"], f["q"], f["t"])[:3], "1080p RayCast")
+    assert rep["rays"] == 1920 * 1080 and rep["hits"] > 0.9 * rep["rays"]
+    big = np.zeros((1081, 1920), np.float32)
+    with pytest.raises(Exception, match="max_image_pixels"):
+        g.Integrate(np.zeros((1081, 1920, 3), np.uint8), big, big, big, cfg.max_depth, f["K"], (f["q"], f["t"]))
+    g.close()
+
+
 def test_config4_full_hd_virtual_views(tg):
     cfg1, cfg4 = synth.config("config1"), synth.config("config4")
     sc, g, o, f = run(tg, cfg1, (0, 5, 10))
