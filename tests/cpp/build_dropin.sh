@@ -25,3 +25,8 @@ g++ -o "$OUT/dropin_native_system" "$OUT/dropin_native_main.o" "$OUT/voxel_types
     -L"$ROOT/disinfect_slam_b200" -ltsdf_b200 -L/usr/local/cuda/lib64 -lcudart -lpthread \
     -Wl,-rpath,'$ORIGIN/../../../disinfect_slam_b200' -Wl,-rpath,/usr/local/cuda/lib64
 echo "built $OUT/dropin_native_system"
+g++ -O2 -std=c++17 -w -I"$ROOT/include/tsdf_b200/compat_system" $INC -c "$HERE/native_errors_main.cc" -o "$OUT/native_errors_main.o"
+g++ -o "$OUT/native_system_errors" "$OUT/native_errors_main.o" "$OUT/voxel_types.o" \
+    -L"$ROOT/disinfect_slam_b200" -ltsdf_b200 -L/usr/local/cuda/lib64 -lcudart -lpthread \
+    -Wl,-rpath,'$ORIGIN/../../../disinfect_slam_b200' -Wl,-rpath,/usr/local/cuda/lib64
+echo "built $OUT/native_system_errors"

@@ -18,6 +18,7 @@ from oracle.oracle import Oracle
 HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(HERE, "cpp", "_build", "dropin_tsdf_module")
 BIN_NATIVE = os.path.join(HERE, "cpp", "_build", "dropin_native_system")
+BIN_ERRORS = os.path.join(HERE, "cpp", "_build", "native_system_errors")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(BIN), reason="tests/cpp/_build not built (needs /root/reference at build time)")]
 
 
@@ -58,3 +59,21 @@ def test_native_tsdf_system(tmp_path, tsdf_lib, extra):
     assert os.path.exists(BIN_NATIVE)
     rep = _run_driver(BIN_NATIVE, tmp_path, 6, extra)
     assert rep["tsdf_bit_exact"] and rep["n_voxels"] > 100 * 512
+
+
+def test_native_tsdf_system_error_paths_and_backpressure(tmp_path, tsdf_lib):
+    """Worker-side engine errors (pool exhausted, bad image type) are rethrown by the next front-end call, the system
+    recovers, and a bounded backlog makes Integrate wait (tests/cpp/native_errors_main.cc)."""
+    assert os.path.exists(BIN_ERRORS)
+    cfg = synth.config("tiny")
+    f = synth.Scene(cfg).frame(0)
+    frames = tmp_path / "one.bin"
+    with open(frames, "wb") as fh:
+        fh.write(struct.pack("<4i3f4f6f", 1, cfg.width, cfg.height, 0, cfg.voxel_size, cfg.truncation, cfg.max_depth,
+                             *[float(np.float32(k)) for k in cfg.K], *([0.0] * 6)))
+        fh.write(np.concatenate([f["q"], f["t"]]).astype(np.float32).tobytes())
+        for k in ("rgb", "depth", "ht", "lt"):
+            fh.write(f[k].tobytes())
+    res = subprocess.run([BIN_ERRORS, str(frames)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "pool exhausted" in res.stdout and "error paths ok" in res.stdout
