@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded single-stream leg at N > 1")
     ap.add_argument("--scale", type=float, default=1.0, help="image scale (debug only; 1.0 = the named config)")
+    ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off"],
+                    help="host waits of the e2e leg yield the CPU (TSDF_FLAG_BLOCKING_SYNC); auto = when the engine threads of all ranks reach half of the cores")
     return ap.parse_args()
 
 
@@ -398,7 +400,9 @@ def main():
     cam = tsdf_grid.CameraParams(streams[0]["K"], H, Wd)
 
     # more synchronously-waiting host threads than cores (e.g. 8 ranks x 4 streams on 16 cores): yield instead of spinning
-    oversubscribed = world * B > 0.75 * (os.cpu_count() or 1)
+    # spinning waits are the fastest while cores are plentiful (1 GPU, 4 threads on 16 cores: 3150 vs 2960 frames/s) and the
+    # slowest once half of them would spin (4 GPUs: 4430 spinning vs 5850 yielding)
+    oversubscribed = world * B >= 0.5 * (os.cpu_count() or 1) if args.blocking_sync == "auto" else args.blocking_sync == "on"
 
     def make_engines(blocking=False):
         return [tsdf_grid.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots,
@@ -613,8 +617,9 @@ def main():
                "api": ("tsdf_integrate_async + tsdf_raycast_async + tsdf_raycast_wait (pipelined, pinned host buffers; every frame's rgba + normal + "
                        "hit depth reach host memory inside the timed region, waited for one frame later)" if pipelined else
                        "tsdf_integrate + tsdf_raycast (synchronous, pinned host buffers)") + ", one host thread per stream"
-                      + (", TSDF_FLAG_BLOCKING_SYNC (more waiting threads than host cores)" if oversubscribed else ""),
-               "ms_per_step": 1e3 * e2e_s / K, "last_frame_rgba_checksum": checksum}
+                      + (", TSDF_FLAG_BLOCKING_SYNC (waiting threads yield: they would occupy half of the host cores or more)" if oversubscribed else ""),
+               "ms_per_step": 1e3 * e2e_s / K, "last_frame_rgba_checksum": checksum, "host_cores": os.cpu_count(),
+               "engine_threads_all_ranks": world * B}
         for g in engs:
             g.close()
         for hb in houts:
