@@ -137,3 +137,29 @@ def save_tsdf_dump(path, records):
 
 def load_tsdf_dump(path):
     return np.fromfile(path, np.float32).reshape(-1, 4)
+
+
+# ---- mesh export (the ROS nodes publish shape_msgs/Mesh: vertices + triangle indices,
+# examples/ros_camera_driver/ros_offline.cc:296-312) ----------------------------------------------------------
+def weld_mesh(tris):
+    """Triangle soup float32 [n, 3, 3] (TSDFGrid.ExtractMesh) -> (vertices float32 [m, 3], triangles int32 [n, 3]).
+    Vertices shared by neighbouring cells are bit-identical by construction, so welding is an exact de-duplication;
+    degenerate triangles (a crossing exactly at a voxel centre) are dropped."""
+    t = np.ascontiguousarray(tris, np.float32).reshape(-1, 3, 3)
+    verts, inv = np.unique(t.reshape(-1, 3).view(np.uint32), axis=0, return_inverse=True)
+    idx = inv.reshape(-1, 3).astype(np.int32)
+    keep = (idx[:, 0] != idx[:, 1]) & (idx[:, 1] != idx[:, 2]) & (idx[:, 0] != idx[:, 2])
+    return verts.view(np.float32), idx[keep]
+
+
+def save_ply(path, tris):
+    """Binary little-endian PLY of the welded mesh."""
+    verts, idx = weld_mesh(tris)
+    with open(path, "wb") as f:
+        f.write((f"ply\nformat binary_little_endian 1.0\nelement vertex {len(verts)}\nproperty float x\nproperty float y\n"
+                 f"property float z\nelement face {len(idx)}\nproperty list uchar int vertex_indices\nend_header\n").encode())
+        f.write(np.ascontiguousarray(verts, "<f4").tobytes())
+        rec = np.empty(len(idx), dtype=[("n", "u1"), ("v", "<i4", 3)])
+        rec["n"], rec["v"] = 3, idx
+        f.write(rec.tobytes())
+    return len(verts), len(idx)

@@ -154,3 +154,21 @@ def mesh_properties(tris):
     balance = np.bincount(inv_e.ravel(), weights=sign, minlength=len(uniq))
     return {"triangles": int(len(t)), "volume": vol, "area": float(area2[area2 > 0].sum() / 2.0), "edges": int(len(uniq)),
             "edges_shared_by_2": int((cnt == 2).sum()), "edges_unbalanced": int((balance != 0).sum()), "vertices": int(len(verts))}
+
+
+def sphere_volume(radius=0.9, vs=0.05, half=3, observed=None):
+    """Hand-built test volume: (2 half)^3 blocks holding the truncated SDF of a sphere (slightly off-centre), every voxel
+    observed unless `observed(centres) -> bool mask` says otherwise.  Returns keys, tsdf, rgbw, voxel_size."""
+    rng = range(-half, half)
+    keys = np.array([[x, y, z] for z in rng for y in rng for x in rng], np.int16)
+    k = np.arange(512)
+    lx, ly, lz = k & 7, (k >> 3) & 7, k >> 6
+    tsdf = np.zeros((len(keys), 512), np.float32)
+    rgbw = np.zeros((len(keys), 512, 4), np.uint8)
+    rgbw[:, :, 3] = 5
+    for i, (bx, by, bz) in enumerate(keys.tolist()):
+        c = (np.stack([bx * 8 + lx, by * 8 + ly, bz * 8 + lz], -1) + 0.5) * vs
+        tsdf[i] = np.clip((np.linalg.norm(c - np.array([0.013, -0.021, 0.007]), axis=1) - radius) / 0.3, -1, 1)
+        if observed is not None:
+            rgbw[i, ~observed(c), 3] = 0
+    return keys, tsdf, rgbw, vs

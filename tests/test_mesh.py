@@ -7,20 +7,7 @@ import pytest
 from oracle import mesh_oracle as M
 
 
-def sphere_blocks(radius=0.9, vs=0.05, half=3, observed=None):
-    rng = range(-half, half)
-    keys = np.array([[x, y, z] for z in rng for y in rng for x in rng], np.int16)
-    k = np.arange(512)
-    lx, ly, lz = k & 7, (k >> 3) & 7, k >> 6
-    tsdf = np.zeros((len(keys), 512), np.float32)
-    rgbw = np.zeros((len(keys), 512, 4), np.uint8)
-    rgbw[:, :, 3] = 5
-    for i, (bx, by, bz) in enumerate(keys.tolist()):
-        c = (np.stack([bx * 8 + lx, by * 8 + ly, bz * 8 + lz], -1) + 0.5) * vs
-        tsdf[i] = np.clip((np.linalg.norm(c - np.array([0.013, -0.021, 0.007]), axis=1) - radius) / 0.3, -1, 1)
-        if observed is not None:
-            rgbw[i, ~observed(c), 3] = 0
-    return keys, tsdf, rgbw, vs
+sphere_blocks = M.sphere_volume
 
 
 def test_oracle_sphere_is_closed_oriented_and_has_the_right_volume():

@@ -69,3 +69,21 @@ def test_replayed_log_matches_oracle(tmp_path, tsdf_lib):
         o.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, np.array(cfg.K, np.float32), f["q"], f["t"])
     assert compare.compare_volumes(g.export(), o.export(), "replayed log")["tsdf_bit_exact"]
     g.close()
+
+
+def test_mesh_welding_and_ply(tmp_path):
+    """ExtractMesh's triangle soup -> indexed mesh (what shape_msgs/Mesh carries, ros_offline.cc:296-312): exact welding of the
+    bit-identical shared vertices; Euler characteristic 2 for the closed sphere of tests/test_mesh.py."""
+    from oracle import mesh_oracle
+    keys, tsdf, rgbw, vs = mesh_oracle.sphere_volume()
+    tris = mesh_oracle.extract_mesh(keys, tsdf, rgbw, vs)
+    verts, idx = replay.weld_mesh(tris)
+    edges = np.unique(np.sort(np.concatenate([idx[:, [0, 1]], idx[:, [1, 2]], idx[:, [2, 0]]]), 1), axis=0)
+    assert len(verts) - len(edges) + len(idx) == 2            # V - E + F of a sphere
+    assert len(idx) <= len(tris) and np.isin(verts[idx].reshape(-1, 9).view(np.uint32), tris.reshape(-1, 9).view(np.uint32)).all()
+    nv, nf = replay.save_ply(tmp_path / "m.ply", tris)
+    raw = open(tmp_path / "m.ply", "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert f"element vertex {nv}".encode() in head and f"element face {nf}".encode() in head
+    assert len(body) == nv * 12 + nf * 13
+    assert np.array_equal(np.frombuffer(body[:nv * 12], "<f4").reshape(nv, 3), verts)
