@@ -60,6 +60,7 @@ SYMBOLS = {
     "tsdf_mesh_device_result": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "tsdf_num_active_blocks": (_i32, [_vp, C.POINTER(_i32)]),
     "tsdf_get_counters": (_i32, [_vp, C.POINTER(Counters)]),
+    "tsdf_get_skip_map_stats": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "tsdf_synchronize": (_i32, [_vp]),
     "tsdf_stream": (_vp, [_vp]),
     "tsdf_block_owner": (_i32, [C.c_int16, C.c_int16, C.c_int16, _i32, _i32]),

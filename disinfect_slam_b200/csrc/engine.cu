@@ -11,6 +11,8 @@
 #include <numeric>
 #include <vector>
 
+#include <unistd.h>
+
 #include "../../include/tsdf_b200.h"
 #include "tsdf_device.cuh"
 #include "tsdf_launch.h"
@@ -58,7 +60,9 @@ struct tsdf_engine {
   PeerView* d_peers = nullptr;       // device array [shard_count]: every shard of a volume sharded over GPUs
   int n_peers = 0;
   void* ipc_opened[kMaxPeers][4] = {};  // pointers obtained from cudaIpcOpenMemHandle (closed at destroy)
-  uint64_t volume_epoch = 1, skip_epoch = 0;
+  uint64_t volume_epoch = 1, skip_epoch = 0;  // host side: a mutating call was enqueued since the map was last looked at
+  int skip_gen = 0;    // number of skip-map build attempts (see skip_fill_kernel)
+  int serial = 0;      // number of mutating calls (frames, allocate / delete lists); DeviceState::serial of the current one
   uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
   // pipelined RayCast (tsdf_raycast_async): two sets of output images (set 0 = the three above, set 1 allocated on first
   // use), rendered on `stream`, copied to the host on `d2h_stream` while the next frame's kernels run
@@ -154,9 +158,15 @@ static int check_frame_args(tsdf_engine* e, const void* a, const void* b, const 
   return TSDF_OK;
 }
 
+static void next_serial(tsdf_engine* e) {
+  e->serial = e->serial >= 0x7FFFFFF0 ? 1 : e->serial + 1;
+  e->S.serial = e->serial;
+}
+
 // kernels of one frame, enqueued on the compute stream; no host synchronisation
 static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned char* rgb, const float* depth,
                           const float* ht, const float* lt, FrameBuf& f) {
+  next_serial(e);
   cudaMemsetAsync(e->S.ctr + C_PER_CALL, 0, sizeof(int) * (C_COUNT - C_PER_CALL), e->stream);
   phase_begin(e, PH_ALLOC, e->stream);
   launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.tex, e->stream);
@@ -193,10 +203,13 @@ static int retire_slot(tsdf_engine* e, int s) {
     e->totals.n_active_post += k.n_active_post; e->totals.n_active_pre += k.n_active_pre;
     e->total_frames++;
   }
-  if (c[C_ERROR] & ERR_POOL) return fail(TSDF_E_POOL_EXHAUSTED, "voxel block pool exhausted (pool_blocks=%d)", e->cfg.pool_blocks);
-  if (c[C_ERROR] & ERR_TABLE) return fail(TSDF_E_TABLE_FULL, "hash table full (table_slots=%d)", e->cfg.table_slots);
   // tombstone garbage collection once live + tombstoned slots exceed half of the table
   if ((unsigned)c[C_NONEMPTY] > (e->S.table_mask + 1) / 2) launch_rehash(e->S, e->num_sms, e->stream);
+  // C_ERROR holds the bits of THIS frame only (it is zeroed with the per-call counters), so an exhaustion is reported
+  // exactly once: the blocks that found no room are missing from this frame, later frames run normally (and succeed
+  // once carving or tsdf_delete_blocks has freed blocks)
+  if (c[C_ERROR] & ERR_POOL) return fail(TSDF_E_POOL_EXHAUSTED, "voxel block pool exhausted (pool_blocks=%d): some blocks of a frame were not allocated", e->cfg.pool_blocks);
+  if (c[C_ERROR] & ERR_TABLE) return fail(TSDF_E_TABLE_FULL, "hash table full (table_slots=%d): some blocks of a frame were not allocated", e->cfg.table_slots);
   return TSDF_OK;
 }
 // host wait for every outstanding tsdf_raycast_async copy
@@ -289,7 +302,8 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
     CUX(cudaMemcpyAsync(e->d_self, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
   }
   CUX(cudaMalloc(&e->skip.dist, kSkipMaxCells)); CUX(cudaMalloc(&e->skip.scratch, kSkipMaxCells));
-  CUX(cudaMalloc(&e->skip.hdr, sizeof(int) * 8));
+  CUX(cudaMalloc(&e->skip.hdr, sizeof(int) * kSkipHdrInts));
+  CUX(cudaMemsetAsync(e->skip.hdr, 0, sizeof(int) * kSkipHdrInts, e->stream));
   CUX(cudaMalloc(&e->skip.index, sizeof(int) * (size_t)kSkipMaxCells));
   const size_t npx = (size_t)cfg.max_image_pixels;
   for (int i = 0; i < 2; ++i) {
@@ -350,8 +364,10 @@ int tsdf_integrate_async(tsdf_handle e, const uint8_t* rgb, const float* depth, 
   CU(cudaSetDevice(e->device));
   const int s = e->cur;
   FrameBuf& f = e->fb[s];
-  rc = retire_slot(e, s);  // the frame two calls ago: bounds the pipeline depth, frees the staging set
-  if (rc) return rc;
+  // the frame two calls ago: bounds the pipeline depth, frees the staging set.  An exhaustion it reports belongs to
+  // THAT frame: the present frame is enqueued all the same and the status is returned afterwards.
+  const int rc_old = retire_slot(e, s);
+  if (rc_old == TSDF_E_CUDA) return rc_old;
   const size_t n = (size_t)w * h;
   // uploads on the copy stream (they overlap the previous frame's kernels on the compute stream)
   phase_begin(e, PH_UPLOAD, e->copy_stream);
@@ -369,15 +385,16 @@ int tsdf_integrate_async(tsdf_handle e, const uint8_t* rgb, const float* depth, 
   e->cur = 1 - s;
   // the host buffers are reusable once the copies have been issued from them
   CU(cudaEventSynchronize(f.uploaded));
-  return TSDF_OK;
+  return rc_old;
 }
 
 int tsdf_integrate(tsdf_handle e, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int w, int h,
                    float max_depth, const float K[4], const float q[4], const float t[3]) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
-  int rc = tsdf_integrate_async(e, rgb, depth, ht, lt, w, h, max_depth, K, q, t);
-  if (rc) return rc;
-  return drain(e);
+  const int rc = tsdf_integrate_async(e, rgb, depth, ht, lt, w, h, max_depth, K, q, t);
+  if (rc == TSDF_E_INVALID || rc == TSDF_E_CUDA || rc == TSDF_E_NO_DEVICE) return rc;
+  const int rc2 = drain(e);  // rc, if set, is the exhaustion of an earlier asynchronous frame: this frame ran
+  return rc2 ? rc2 : rc;
 }
 
 int tsdf_integrate_device(tsdf_handle e, const void* d_rgb, const void* d_depth, const void* d_ht, const void* d_lt, int w,
@@ -387,15 +404,15 @@ int tsdf_integrate_device(tsdf_handle e, const void* d_rgb, const void* d_depth,
   CU(cudaSetDevice(e->device));
   const int s = e->cur;
   FrameBuf& f = e->fb[s];
-  rc = retire_slot(e, s);
-  if (rc) return rc;
+  const int rc_old = retire_slot(e, s);  // an exhaustion of the frame two calls ago: reported below, this frame still runs
+  if (rc_old == TSDF_E_CUDA) return rc_old;
   if (after_event) CU(cudaStreamWaitEvent(e->stream, (cudaEvent_t)after_event, 0));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
   enqueue_frame(e, P, (const unsigned char*)d_rgb, (const float*)d_depth, (const float*)d_ht, (const float*)d_lt, f);
   CU(cudaGetLastError());
   e->last_slot = s;
   e->cur = 1 - s;
-  return TSDF_OK;
+  return rc_old;
 }
 
 int tsdf_synchronize(tsdf_handle e) {
@@ -413,8 +430,9 @@ int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const floa
   CU(cudaSetDevice(e->device));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
   phase_begin(e, PH_RAYCAST, e->stream);
-  if (e->skip_epoch != e->volume_epoch) {  // block set may have changed since the map was built
-    launch_build_skip_map(e->d_self, 1, e->skip, e->num_sms, e->stream);
+  if (e->skip_epoch != e->volume_epoch) {  // a mutating call ran since the map was built; the kernels themselves
+    // return at once if that call turned out not to change the block set (device-side serial, skip_fill_kernel)
+    launch_build_skip_map(e->d_self, 1, e->skip, ++e->skip_gen, true, e->num_sms, e->stream);
     e->skip_epoch = e->volume_epoch;
   }
   launch_raycast(e->S, P, e->truncation / 2, e->skip, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
@@ -497,6 +515,8 @@ namespace {
 struct IpcBlob {
   cudaIpcMemHandle_t table, block_key, voxels, ctr;
   uint32_t table_mask; int32_t pool_blocks, shard_rank, shard_count, shard_shift, device;
+  int64_t pid;    // exporting process: CUDA IPC handles cannot be opened by the process that made them, so shards
+  void* raw[4];   //   living in the attaching process (one host thread per GPU) are reached through these pointers
 };
 static_assert(sizeof(IpcBlob) <= TSDF_IPC_BLOB_BYTES, "TSDF_IPC_BLOB_BYTES too small");
 }  // namespace
@@ -509,6 +529,8 @@ int tsdf_ipc_export(tsdf_handle e, void* blob) {
   CU(cudaIpcGetMemHandle(&b.voxels, e->S.voxels)); CU(cudaIpcGetMemHandle(&b.ctr, e->S.ctr));
   b.table_mask = e->S.table_mask; b.pool_blocks = e->S.pool_blocks; b.shard_rank = e->S.shard_rank;
   b.shard_count = e->S.shard_count; b.shard_shift = e->S.shard_shift; b.device = e->device;
+  b.pid = (int64_t)getpid();
+  b.raw[0] = e->S.table; b.raw[1] = e->S.block_key; b.raw[2] = e->S.voxels; b.raw[3] = e->S.ctr;
   memset(blob, 0, TSDF_IPC_BLOB_BYTES);
   memcpy(blob, &b, sizeof(b));
   return TSDF_OK;
@@ -539,10 +561,22 @@ int tsdf_ipc_attach(tsdf_handle e, int world, const void* blobs) {
     if (r == e->S.shard_rank) { views[r] = self_view(e); continue; }
     void* p[4] = {};
     const cudaIpcMemHandle_t* hs[4] = {&b.table, &b.block_key, &b.voxels, &b.ctr};
-    for (int k = 0; k < 4; ++k) {
-      if (e->ipc_opened[r][k]) { cudaIpcCloseMemHandle(e->ipc_opened[r][k]); e->ipc_opened[r][k] = nullptr; }
-      CU(cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess));
-      e->ipc_opened[r][k] = p[k];
+    if (b.pid == (int64_t)getpid()) {  // a shard of this very process: plain peer access, no IPC mapping
+      if (b.device != e->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, e->device, b.device));
+        if (!can) return fail(TSDF_E_CUDA, "device %d cannot access device %d as a peer", e->device, b.device);
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(TSDF_E_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", b.device, cudaGetErrorString(pe));
+        cudaGetLastError();
+      }
+      for (int k = 0; k < 4; ++k) p[k] = b.raw[k];
+    } else {
+      for (int k = 0; k < 4; ++k) {
+        if (e->ipc_opened[r][k]) { cudaIpcCloseMemHandle(e->ipc_opened[r][k]); e->ipc_opened[r][k] = nullptr; }
+        CU(cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess));
+        e->ipc_opened[r][k] = p[k];
+      }
     }
     views[r].table = (const Slot*)p[0]; views[r].table_mask = b.table_mask; views[r].block_key = (const u64*)p[1];
     views[r].voxels = (const unsigned char*)p[2]; views[r].ctr = (const int*)p[3];
@@ -577,7 +611,7 @@ int tsdf_raycast_shared(tsdf_handle e, float max_depth, int w, int h, const floa
   CU(cudaSetDevice(e->device));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
   phase_begin(e, PH_RAYCAST, e->stream);
-  launch_build_skip_map(e->d_peers, e->n_peers, e->skip, e->num_sms, e->stream);  // union of every shard's blocks
+  launch_build_skip_map(e->d_peers, e->n_peers, e->skip, ++e->skip_gen, false, e->num_sms, e->stream);  // union of every shard's blocks
   e->skip_epoch = 0;  // the map no longer describes this engine alone
   launch_raycast_shared(e->d_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0),
                         (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, e->stream);
@@ -714,6 +748,18 @@ int tsdf_num_active_blocks(tsdf_handle e, int* n) {
   return TSDF_OK;
 }
 
+int tsdf_get_skip_map_stats(tsdf_handle e, int64_t* attempts, int64_t* rebuilds) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(e->h_scalar, e->skip.hdr + 12, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CU(wait_stream(e, e->stream));
+  if (attempts) *attempts = e->skip_gen;
+  if (rebuilds) *rebuilds = e->h_scalar[0];
+  return TSDF_OK;
+}
+
 int tsdf_get_counters(tsdf_handle e, tsdf_counters* out) {
   if (!e || !out) return fail(TSDF_E_INVALID, "null argument");
   CU(cudaSetDevice(e->device));
@@ -746,6 +792,8 @@ int tsdf_allocate_blocks(tsdf_handle e, const int16_t* keys, int n) {
   int rc = drain(e); if (rc) return rc;
   DevBuf<short> d; CU(d.alloc(3 * (size_t)n));
   if (n) CU(cudaMemcpyAsync(d.p, keys, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
+  next_serial(e);
+  CU(cudaMemsetAsync(e->S.ctr + C_PER_CALL, 0, sizeof(int) * (C_COUNT - C_PER_CALL), e->stream));
   launch_allocate_list(e->S, d.p, n, e->stream);
   e->volume_epoch++;
   return after_mutation(e);
@@ -756,6 +804,8 @@ int tsdf_delete_blocks(tsdf_handle e, const int16_t* keys, int n) {
   int rc = drain(e); if (rc) return rc;
   DevBuf<short> d; CU(d.alloc(3 * (size_t)n));
   if (n) CU(cudaMemcpyAsync(d.p, keys, sizeof(short) * 3 * n, cudaMemcpyHostToDevice, e->stream));
+  next_serial(e);
+  CU(cudaMemsetAsync(e->S.ctr + C_PER_CALL, 0, sizeof(int) * (C_COUNT - C_PER_CALL), e->stream));
   launch_delete_list(e->S, d.p, n, e->stream);
   e->volume_epoch++;
   return after_mutation(e);

@@ -101,7 +101,7 @@ __global__ void allocate_list_kernel(DeviceState S, const short* __restrict__ ke
   if (i >= n) return;
   const u64 key = pack_key(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]);
   if (S.shard_count > 1 && owner_of(key, S.shard_count, S.shard_shift) != (unsigned)S.shard_rank) return;
-  if (table_insert(S, key) == 1) atomicAdd(&S.ctr[C_NNEW], 1);
+  if (table_insert(S, key) == 1) { atomicAdd(&S.ctr[C_NNEW], 1); mark_block_set_changed(S); }
 }
 // blocks inserted outside Integrate are materialised immediately (the integrate kernel normally
 // does that in registers): clear the NEW flag and write the acquire-time defaults
@@ -115,7 +115,7 @@ __global__ void materialise_new_kernel(DeviceState S) {
 __global__ void delete_list_kernel(DeviceState S, const short* __restrict__ keys, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (table_erase(S, pack_key(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]))) atomicAdd(&S.ctr[C_NCARVED], 1);
+  if (table_erase(S, pack_key(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]))) { atomicAdd(&S.ctr[C_NCARVED], 1); mark_block_set_changed(S); }
 }
 __global__ void retrieve_list_kernel(DeviceState S, const short* __restrict__ pts, int n, float* tsdf, unsigned* rgbw,
                                      float* prob, int* found) {

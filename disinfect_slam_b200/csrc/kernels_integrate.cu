@@ -429,8 +429,8 @@ __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kerne
         n_done = (old & 0xFF) + 1; n_far = (old >> 8) + far;
       }
       if (n_done == kItemsPerBlock) {  // this item completed the block
-        if (n_far == kItemsPerBlock) { table_erase(S, bk & kKeyMask); ++n_carved_thread; }
-        else if (is_new) S.block_key[idx] = bk & kKeyMask;
+        if (n_far == kItemsPerBlock) { table_erase(S, bk & kKeyMask); ++n_carved_thread; if (!is_new) mark_block_set_changed(S); }
+        else if (is_new) { S.block_key[idx] = bk & kKeyMask; mark_block_set_changed(S); }
       }
     }
     it = it_next; idx = idx_next; bk = bk_next;

@@ -27,7 +27,21 @@ namespace tsdf {
 // ------------------------------------------------------------------------------------------
 // header from the AABB counters + fill with the cap.  Every thread derives the same header (a handful of integer
 // operations) so that no separate one-thread launch is needed; thread 0 publishes it for the later kernels.
-__global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M) {
+// Build attempts are numbered (gen) by the host.  With `lazy` set, attempt g first compares the serial of the last call
+// that changed the block set (ctr[C_DIRTY], written by table_insert / table_erase) with the one recorded by attempt
+// g - 1: equal means the map is still exact and all five kernels return at once -- a frame that neither allocated nor
+// carved a block (a static camera, a converged scene) costs five empty launches instead of a rebuild.  The two
+// records alternate between hdr[8] / hdr[9] so that no thread reads a word another thread of the same kernel writes;
+// the verdict for the four later kernels goes to hdr[10 + (g & 1)].
+__global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M, int gen, int lazy) {
+  if (lazy) {
+    const int serial = shards[0].ctr[C_DIRTY];
+    const bool rebuild = M.hdr[8 + ((gen - 1) & 1)] != serial;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { M.hdr[8 + (gen & 1)] = serial; M.hdr[10 + (gen & 1)] = rebuild ? 1 : 0; if (rebuild) M.hdr[12]++; }
+    if (!rebuild) return;
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    M.hdr[8 + (gen & 1)] = -1; M.hdr[10 + (gen & 1)] = 1; M.hdr[12]++;  // -1 never equals a serial: the next lazy attempt rebuilds
+  }
   // AABB of every shard's inserts (one shard = the engine itself; several = a volume sharded over GPUs, whose
   // counters are read over NVLink)
   int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, z0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF, y1 = -0x7FFFFFFF, z1 = -0x7FFFFFFF;
@@ -60,7 +74,8 @@ __global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M) {
+__global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M, int gen) {
+  if (!M.hdr[10 + (gen & 1)]) return;
   const int ox = M.hdr[0], oy = M.hdr[1], oz = M.hdr[2], nx = M.hdr[3], ny = M.hdr[4], shift = M.hdr[6];
   for (int r = 0; r < n_shards; ++r) {
     const int hw = shards[r].ctr[C_HIGH_WATER];
@@ -82,7 +97,8 @@ __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restri
 // All 2 * (cap - 1) neighbour reads of a cell are independent (no early exit), so they are in flight together.
 template <int AXIS>
 __global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigned char* __restrict__ in,
-                                                        unsigned char* __restrict__ out) {
+                                                        unsigned char* __restrict__ out, int gen) {
+  if (!M.hdr[10 + (gen & 1)]) return;
   const int nx = M.hdr[3], ny = M.hdr[4], nz = M.hdr[5], n = M.hdr[7];
   const int len = AXIS == 0 ? nx : AXIS == 1 ? ny : nz;
   const int stride = AXIS == 0 ? 1 : AXIS == 1 ? nx : nx * ny;
@@ -101,12 +117,12 @@ __global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigne
   }
 }
 
-void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int num_sms, cudaStream_t st) {
-  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(shards, n_shards, M);
-  skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(shards, n_shards, M);
-  skip_pass_kernel<0><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch);
-  skip_pass_kernel<1><<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist);
-  skip_pass_kernel<2><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch);
+void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int gen, bool lazy, int num_sms, cudaStream_t st) {
+  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(shards, n_shards, M, gen, lazy && n_shards == 1 ? 1 : 0);
+  skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(shards, n_shards, M, gen);
+  skip_pass_kernel<0><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, gen);
+  skip_pass_kernel<1><<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist, gen);
+  skip_pass_kernel<2><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, gen);
   // result is in M.scratch; the raycast kernel is launched with the two pointers swapped
 }
 

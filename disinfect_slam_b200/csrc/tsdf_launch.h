@@ -15,7 +15,8 @@ void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const in
                             int num_sms, cudaStream_t st);
 
 // kernels_raycast.cu
-void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int num_sms, cudaStream_t st);
+void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int gen, bool lazy, int num_sms,
+                           cudaStream_t st);
 void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
                            const SkipMap& M, int row0, int rows, uchar4* rgba, uchar4* normal, float* hit_depth,
                            cudaStream_t st);

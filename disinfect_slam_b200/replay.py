@@ -1,8 +1,8 @@
 """On-disk formats of the reference's offline TSDF replay, so recorded sequences can
 drive the engine and volumes can be dumped the way the reference does:
 
-  <logdir>/trajectory.txt         one line per frame: `id` + 12 floats = row-major 3x4 cam_T_world
-                                  (examples/tsdf/offline.cc:45-64)
+  <logdir>/trajectory.txt         one line per frame: `id` + 12 floats = row-major 3x4 posecam_T_world, left-multiplied
+                                  by the config's `Extrinsics` to give cam_T_world (examples/tsdf/offline.cc:36-64)
   <logdir>/<id>_rgb.png           8-bit colour, BGR on disk as cv::imwrite leaves it (offline.cc:72,163)
   <logdir>/<id>_depth.png         16-bit, metres = value / depthmap_factor (offline.cc:73,77)
   <logdir>/<id>_ht.png, _no_ht.png  16-bit probabilities, value / 65535; absent -> ht = 0, lt = 1 (offline.cc:74-83)
@@ -55,16 +55,63 @@ def rotation_from_quat(q):
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], np.float64)
 
 
-def read_trajectory(logdir):
-    """[(id, q_xyzw float32[4], t float32[3])] from trajectory.txt."""
+def _cross(a, b):
+    f = np.float32
+    return np.array([f(f(a[1] * b[2]) - f(a[2] * b[1])), f(f(a[2] * b[0]) - f(a[0] * b[2])), f(f(a[0] * b[1]) - f(a[1] * b[0]))],
+                    np.float32)
+
+
+def quat_rotate(q, v):
+    """Eigen 3.3 QuaternionBase::_transformVector in float32 (q = x, y, z, w): uv = 2 (q.vec x v); v + w uv + q.vec x uv."""
+    q, v = np.asarray(q, np.float32), np.asarray(v, np.float32)
+    uv = _cross(q[:3], v)
+    uv = (uv + uv).astype(np.float32)
+    c = _cross(q[:3], uv)
+    return ((v + (q[3] * uv).astype(np.float32)).astype(np.float32) + c).astype(np.float32)
+
+
+def quat_multiply(a, b):
+    """Eigen 3.3 quaternion product a * b, generic (scalar) path, float32, operands as (x, y, z, w)."""
+    f = np.float32
+    ax, ay, az, aw = (f(v) for v in a)
+    bx, by, bz, bw = (f(v) for v in b)
+    w = f(f(f(f(aw * bw) - f(ax * bx)) - f(ay * by)) - f(az * bz))
+    x = f(f(f(f(aw * bx) + f(ax * bw)) + f(ay * bz)) - f(az * by))
+    y = f(f(f(f(aw * by) + f(ay * bw)) + f(az * bx)) - f(ax * bz))
+    z = f(f(f(f(aw * bz) + f(az * bw)) + f(ax * by)) - f(ay * bx))
+    return np.array([x, y, z, w], np.float32)
+
+
+def se3_compose(a, b):
+    """SE3<float>::operator* (utils/cuda/lie_group.cuh:38-40): (Ra Rb, Ra tb + ta); poses as (q_xyzw, t)."""
+    (qa, ta), (qb, tb) = a, b
+    return quat_multiply(qa, qb), (quat_rotate(qa, tb) + np.asarray(ta, np.float32)).astype(np.float32)
+
+
+def se3_from_matrix(m):
+    """SE3<float>(Matrix4f / Matrix<float, 3, 4>) (lie_group.cuh:16-20): rotation block -> quaternion, last column."""
+    m = np.asarray(m, np.float32).reshape(-1, 4)
+    return quat_from_rotation(m[:3, :3]), m[:3, 3].copy()
+
+
+def read_trajectory(logdir, extrinsics=None):
+    """[(id, q_xyzw float32[4], t float32[3])] = cam_T_world of every frame of trajectory.txt.
+
+    The file stores posecam_T_world (the tracking camera); the reference turns it into the depth camera's pose with
+    the config's `Extrinsics` (row-major 4x4, depthcam_T_posecam): `extrinsics * SE3<float>(tmp)`
+    (examples/tsdf/offline.cc:36-62).  `extrinsics` = that 4x4 (any shape with 16 values) or None for identity, which is
+    what get_extrinsics returns when the key is absent.  All four shipped L515 configs carry a non-identity one."""
+    ext = None if extrinsics is None else se3_from_matrix(np.asarray(extrinsics, np.float32).reshape(4, 4))
     out = []
     with open(os.path.join(logdir, "trajectory.txt")) as fh:
         for line in fh:
             v = line.split()
             if len(v) < 13:
                 continue
-            m = np.array([float(s) for s in v[1:13]], np.float32).reshape(3, 4)
-            out.append((int(v[0]), quat_from_rotation(m[:, :3]), m[:, 3].copy()))
+            q, t = se3_from_matrix(np.array([float(s) for s in v[1:13]], np.float32).reshape(3, 4))
+            if ext is not None:
+                q, t = se3_compose(ext, (q, t))
+            out.append((int(v[0]), q, t))
     return out
 
 
@@ -92,9 +139,9 @@ def read_frame(logdir, frame_id, depthmap_factor):
     return dict(rgb=rgb, depth=depth, ht=ht, lt=lt)
 
 
-def read_log(logdir, depthmap_factor):
+def read_log(logdir, depthmap_factor, extrinsics=None):
     """Iterate the frames of a reference-format log: dicts with rgb, depth, ht, lt, q, t, id."""
-    for frame_id, q, t in read_trajectory(logdir):
+    for frame_id, q, t in read_trajectory(logdir, extrinsics):
         f = read_frame(logdir, frame_id, depthmap_factor)
         f.update(q=q, t=t, id=frame_id)
         yield f
@@ -119,10 +166,11 @@ def write_log(logdir, frames, depthmap_factor):
                     cv2.imwrite(os.path.join(logdir, f"{i}_{suffix}.png"), p16)
 
 
-def replay(grid, logdir, depthmap_factor, intrinsics, max_depth=4.0, limit=None):
-    """Integrate every frame of a log into `grid` (a TSDFGrid); returns the number of frames integrated."""
+def replay(grid, logdir, depthmap_factor, intrinsics, max_depth=4.0, limit=None, extrinsics=None):
+    """Integrate every frame of a log into `grid` (a TSDFGrid); returns the number of frames integrated.
+    `extrinsics`: the config's `Extrinsics` 4x4 (see read_trajectory)."""
     n = 0
-    for f in read_log(logdir, depthmap_factor):
+    for f in read_log(logdir, depthmap_factor, extrinsics):
         grid.Integrate(f["rgb"], f["depth"], f["ht"], f["lt"], max_depth, intrinsics, (f["q"], f["t"]))
         n += 1
         if limit is not None and n >= limit:

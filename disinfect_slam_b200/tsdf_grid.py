@@ -248,6 +248,12 @@ class TSDFGrid:
         check(self.L.tsdf_get_counters(self.h, C.byref(c)))
         return {k: int(getattr(c, k)) for k, _ in Counters._fields_ if k != "reserved"}
 
+    def skip_map_stats(self):
+        """(build attempts, real rebuilds) of the RayCast skip map."""
+        a, r = C.c_int64(0), C.c_int64(0)
+        check(self.L.tsdf_get_skip_map_stats(self.h, C.byref(a), C.byref(r)))
+        return int(a.value), int(r.value)
+
     def synchronize(self):
         check(self.L.tsdf_synchronize(self.h))
 

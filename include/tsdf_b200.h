@@ -94,7 +94,10 @@ int tsdf_integrate(tsdf_handle h, const uint8_t* rgb, const float* depth, const 
                    const float t_xyz[3]);
 /* Pipelined variant: returns as soon as the host buffers have been consumed (copied to one of
  * two device staging sets); the kernels of this frame overlap the next call's upload.  Call
- * tsdf_synchronize() before reading counters / results.  Same arithmetic as tsdf_integrate. */
+ * tsdf_synchronize() before reading counters / results.  Same arithmetic as tsdf_integrate.
+ * Errors of the pipelined calls: TSDF_E_POOL_EXHAUSTED / TSDF_E_TABLE_FULL describe a frame submitted two calls
+ * earlier (the one whose staging set this call reuses) and are reported exactly once; the frame passed to THIS call
+ * has been enqueued all the same, and later frames run normally once blocks have been freed. */
 int tsdf_integrate_async(tsdf_handle h, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
                          int width, int height, float max_depth, const float K[4], const float q_xyzw[4],
                          const float t_xyz[3]);
@@ -187,6 +190,11 @@ int tsdf_mesh_device_result(tsdf_handle h, const void** d_out_xyz, int64_t* n_tr
 /* VoxelHashTable::NumActiveBlock()                      utils/tsdf/voxel_hash.cu:200 */
 int tsdf_num_active_blocks(tsdf_handle h, int* n);
 int tsdf_get_counters(tsdf_handle h, tsdf_counters* out);
+/* RayCast keeps an empty-space skip map over the block set (no reference counterpart: ray_cast_kernel,
+ * voxel_tsdf.cu:232-307, probes the table at every sample).  *attempts = how often a RayCast found that a mutating
+ * call had run since the map was built, *rebuilds = how often the block set had really changed (frames that only
+ * allocate-and-carve the same edge blocks leave it valid). */
+int tsdf_get_skip_map_stats(tsdf_handle h, int64_t* attempts, int64_t* rebuilds);
 int tsdf_synchronize(tsdf_handle h);
 /* cudaStream_t the engine enqueues on (for event interop with callers that own device data). */
 void* tsdf_stream(tsdf_handle h);
@@ -201,18 +209,21 @@ int tsdf_block_owner(int16_t bx, int16_t by, int16_t bz, int shard_count, int sh
 
 /* Parity / unit-test access (what utils/tests/voxel_hash_test.cu:36-55 does with its own
  * Allocate / Retrieve / Assignment kernels, and voxel_mem_test.cu with Aquire/Release).
- * keys / points are int16 triples. */
-int tsdf_allocate_blocks(tsdf_handle h, const int16_t* block_keys, int n); /* VoxelHashTable::Allocate, voxel_hash.cu:58 */
-int tsdf_delete_blocks(tsdf_handle h, const int16_t* block_keys, int n);   /* VoxelHashTable::Delete,   voxel_hash.cu:122 */
+ * keys / points are int16 triples.  Entry points marked TSDF_TEST_API exist for the test suites and for
+ * checkpoint-style export: they drain the pipeline and allocate scratch device memory on every call, so they do
+ * not belong in a per-frame loop.  Duplicate keys in one list are allowed (each block is inserted / released once). */
+#define TSDF_TEST_API
+TSDF_TEST_API int tsdf_allocate_blocks(tsdf_handle h, const int16_t* block_keys, int n); /* VoxelHashTable::Allocate, voxel_hash.cu:58 */
+TSDF_TEST_API int tsdf_delete_blocks(tsdf_handle h, const int16_t* block_keys, int n);   /* VoxelHashTable::Delete,   voxel_hash.cu:122 */
 /* VoxelHashTable::Retrieve<T>, voxel_hash.cuh:104-113: absent -> tsdf 1, rgbw 0, prob 0, found 0 */
-int tsdf_retrieve_voxels(tsdf_handle h, const int16_t* points, int n, float* tsdf, uint8_t* rgbw /* n x 4 */,
+TSDF_TEST_API int tsdf_retrieve_voxels(tsdf_handle h, const int16_t* points, int n, float* tsdf, uint8_t* rgbw /* n x 4 */,
                          float* prob, int32_t* found);
 /* VoxelHashTable::RetrieveMutable + store, voxel_hash.cuh:124-161; any value pointer may be NULL */
-int tsdf_assign_voxels(tsdf_handle h, const int16_t* points, int n, const float* tsdf, const uint8_t* rgbw,
+TSDF_TEST_API int tsdf_assign_voxels(tsdf_handle h, const int16_t* points, int n, const float* tsdf, const uint8_t* rgbw,
                        const float* prob);
 /* All active blocks in canonical order (ascending z, y, x block coordinate): keys int16[n][3],
  * tsdf float[n][512], rgbw uint8[n][512][4] (r,g,b,weight), prob float[n][512]; any may be NULL. */
-int tsdf_export_blocks(tsdf_handle h, int16_t* keys, float* tsdf, uint8_t* rgbw, float* prob, int cap_blocks,
+TSDF_TEST_API int tsdf_export_blocks(tsdf_handle h, int16_t* keys, float* tsdf, uint8_t* rgbw, float* prob, int cap_blocks,
                        int* n_blocks);
 
 /* Pinned host memory helpers so callers can hand tsdf_integrate DMA-able buffers. */

@@ -21,8 +21,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from disinfect_slam_b200 import synth  # noqa: E402
 
-CONFIG, N_FRAMES, BBOX = "tiny", 4, (-1.0, 1.5, -1.2, 0.9, -2.5, 0.4)
+CONFIG, BBOX = "tiny", (-1.0, 1.5, -1.2, 0.9, -2.5, 0.4)
 VIRTUAL = dict(width=96, height=64, K=(80.0, 80.0, 47.5, 31.5))
+# Frame sequence: four frames of the moving camera, then the camera dwells on three neighbouring poses (60 frames) long enough for
+# the weight clamp `min(roundf(w), 40)` (voxel_tsdf.cu:192) and dozens of colour re-quantisations to act.  Full
+# per-block digests are stored at the SNAPSHOT frames only; the block-coordinate set is stored for every frame (as
+# a delta), because a block the reference allocated late is "don't care" from that frame on.
+SEQUENCE = [0, 1, 2, 3] + [i % 3 for i in range(4, 64)]
+SNAPSHOTS = (0, 1, 2, 3, 15, 31, 47, 63)
+N_FRAMES = len(SEQUENCE)
+
+
+def key_rows(keys):
+    return set(map(tuple, np.asarray(keys).reshape(-1, 3).tolist()))
+
+
+def rows_array(rows):
+    return np.array(sorted(rows), np.int16).reshape(-1, 3)
 
 
 def digest_rows(a):
@@ -45,10 +60,18 @@ def main(out):
     sc = synth.Scene(cfg)
     r = RefTSDFGrid(cfg.voxel_size, cfg.truncation, parity=True)
     d = {"config": np.array(CONFIG), "n_frames": np.array(N_FRAMES), "bbox": np.array(BBOX, np.float32)}
+    d["sequence"] = np.array(SEQUENCE, np.int32)
+    d["snapshots"] = np.array(SNAPSHOTS, np.int32)
     rng = np.random.RandomState(7)
+    prev = set()
     for i in range(N_FRAMES):
-        f = sc.frame(i)
+        f = sc.frame(SEQUENCE[i])
         r.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"])
+        now = key_rows(r.export(voxels=False)[0])
+        d[f"added_{i}"], d[f"removed_{i}"] = rows_array(now - prev), rows_array(prev - now)
+        prev = now
+        if i not in SNAPSHOTS:
+            continue
         keys, tsdf, rgbw, prob = r.export()
         d[f"keys_{i}"] = keys
         d[f"tsdf_digest_{i}"] = digest_rows(tsdf)
@@ -58,6 +81,7 @@ def main(out):
         rgbw[rgbw[..., 3] == 0] = 0
         d[f"rgbw_digest_{i}"] = digest_rows(rgbw)
         d[f"weight_sum_{i}"] = rgbw[..., 3].astype(np.int64).sum(1)
+        d[f"weight40_frac_{i}"] = np.array((rgbw[..., 3] == 40).sum() / max((rgbw[..., 3] > 0).sum(), 1))
         sb = rng.randint(0, len(keys), 4000)
         sv = rng.randint(0, 512, 4000)
         d[f"prob_sample_idx_{i}"] = np.stack([sb, sv], 1).astype(np.int32)
@@ -77,7 +101,8 @@ def main(out):
             d["gather_bound_n_0"] = np.array(n)
             d["num_active_0"] = np.array(r.num_active())
     np.savez_compressed(out, **d)
-    print("wrote", out, os.path.getsize(out), "bytes;", {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k.startswith("keys")})
+    print("wrote", out, os.path.getsize(out), "bytes;", {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k.startswith("keys")},
+          {k: float(v) for k, v in d.items() if k.startswith("weight40")})
 
 
 if __name__ == "__main__":

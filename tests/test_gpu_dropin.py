@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(HERE, "cpp", "_build", "dropin_tsdf_module")
 BIN_NATIVE = os.path.join(HERE, "cpp", "_build", "dropin_native_system")
 BIN_ERRORS = os.path.join(HERE, "cpp", "_build", "native_system_errors")
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(BIN), reason="tests/cpp/_build not built (needs /root/reference at build time)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("dropin_binaries")]  # missing binaries FAIL (conftest.py), they do not skip
 
 
 def _run_driver(binary, tmp_path, n_frames, extra_frame_without_probs):

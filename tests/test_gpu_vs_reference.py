@@ -12,7 +12,7 @@ import pytest
 from disinfect_slam_b200 import synth
 from oracle import compare, ref_cuda
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_cuda.available(True), reason="oracle/_ref not built (needs /root/reference at build time)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("ref_parity_lib")]  # a missing oracle/_ref FAILS (conftest.py), it does not skip
 
 
 def keyset(k):

@@ -43,24 +43,37 @@ def masked_rgbw(rgbw):
 
 
 def test_integrate_matches_reference_cuda(gold):
+    """Every frame of the golden sequence (4 moving + 60 dwelling frames): block sets on every frame, bit-exact TSDF /
+    RGBW digests at the snapshot frames -- including the steady state, where the weight clamp at 40
+    (voxel_tsdf.cu:192) has acted on a large share of the voxels."""
     cfg = synth.config(str(gold["config"]))
     sc = synth.Scene(cfg)
     o = Oracle(cfg.voxel_size, cfg.truncation)
-    dont_care = set()
+    seq, snaps = [int(v) for v in gold["sequence"]], {int(v) for v in gold["snapshots"]}
+    assert len(seq) == int(gold["n_frames"]) >= 30
+    dont_care, rs = set(), set()
     n_clean_total = 0
-    for i in range(int(gold["n_frames"])):
-        f = sc.frame(i)
+    frames = {i: sc.frame(i) for i in set(seq)}
+    for i, fi in enumerate(seq):
+        f = frames[fi]
         o.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"])
+        rs = (rs | keyset(gold[f"added_{i}"])) - keyset(gold[f"removed_{i}"])
+        if i not in snaps:
+            os_ = keyset(o.export(voxels=False)[0])
+            assert rs <= os_, f"frame {i}: the reference holds blocks the ideal semantics do not: {sorted(rs - os_)[:5]}"
+            dont_care |= (os_ - rs)
+            continue
         ok, ot, oc, op = o.export()
         rk = gold[f"keys_{i}"]
-        rs, os_ = keyset(rk), keyset(ok)
+        os_ = keyset(ok)
+        assert keyset(rk) == rs
         assert rs <= os_, f"frame {i}: the reference holds blocks the ideal semantics do not: {sorted(rs - os_)[:5]}"
         dont_care |= (os_ - rs)
         assert len(dont_care) <= 0.08 * len(os_), (i, len(dont_care), len(os_))
         oi = {k: j for j, k in enumerate(map(tuple, ok.tolist()))}
         clean = np.array([tuple(k) not in dont_care for k in rk.tolist()])
         sel = np.array([oi[tuple(k)] for k in rk.tolist()])
-        assert clean.sum() >= 0.95 * len(rk)
+        assert clean.sum() >= 0.92 * len(rk)
         n_clean_total += int(clean.sum())
         # bit-exact TSDF and weight/colour planes of every clean block
         assert np.array_equal(digest_rows(ot[sel])[clean], gold[f"tsdf_digest_{i}"][clean]), f"frame {i}: TSDF planes differ"
@@ -73,7 +86,12 @@ def test_integrate_matches_reference_cuda(gold):
         assert dp.max() <= compare.PROB_TOL, dp.max()
         if i == 0:
             assert not dont_care or clean.all()  # on the first frame every block the reference holds is clean
-    assert n_clean_total > 4000
+    assert n_clean_total > 8000
+    # the steady state really was reached, in the reference's own volume and in the oracle's
+    last = max(snaps)
+    assert float(gold[f"weight40_frac_{last}"]) > 0.2
+    w = oc[sel][clean][..., 3]
+    assert (w == 40).sum() > 0.2 * (w > 0).sum() and w.max() == 40
 
 
 def test_raycast_and_gather_match_reference_cuda(gold):

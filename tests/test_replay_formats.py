@@ -43,6 +43,44 @@ def test_log_round_trip(tmp_path):
     assert (g["ht"] == 0).all() and (g["lt"] == 1).all()
 
 
+# `Extrinsics` of configs/zed_native_l515.yaml:19-24 (l515 -> zed, about 4 cm and 2 degrees)
+L515_EXTRINSICS = [0.9995, -0.0097, 0.0289, -37.172e-3, 0.009, 0.9997, 0.0247, -22.6717e-3,
+                   -0.0291, -0.0245, 0.9993, 2.4699e-3, 0, 0, 0, 1]
+
+
+def test_trajectory_extrinsics_premultiply(tmp_path):
+    """read_trajectory(extrinsics) = extrinsics * SE3(row) (examples/tsdf/offline.cc:36-62), checked against the
+    float64 matrix product; identity / None leave the poses unchanged."""
+    cfg = synth.config("tiny")
+    sc = synth.Scene(cfg)
+    frames = [sc.frame(i) for i in range(4)]
+    replay.write_log(str(tmp_path), frames, cfg.depth_factor)
+    plain = replay.read_trajectory(str(tmp_path))
+    ident = replay.read_trajectory(str(tmp_path), np.eye(4))
+    ext = replay.read_trajectory(str(tmp_path), L515_EXTRINSICS)
+    E = np.array(L515_EXTRINSICS, np.float64).reshape(4, 4)
+    # the YAML matrix is only approximately a rotation: SE3(Matrix4f) goes through a quaternion, which normalises nothing
+    # but drops the non-rotation part, so compare against the rotation that quaternion stands for
+    qe, te = replay.se3_from_matrix(E)
+    Re = replay.rotation_from_quat(qe.astype(np.float64) / np.linalg.norm(qe.astype(np.float64)))
+    moved = 0.0
+    for (i0, q0, t0), (i1, q1, t1), (i2, q2, t2) in zip(plain, ident, ext):
+        assert i0 == i1 == i2
+        assert min(np.abs(q1 - q0).max(), np.abs(q1 + q0).max()) < 1e-6 and np.abs(t1 - t0).max() < 1e-6
+        R0 = replay.rotation_from_quat(q0.astype(np.float64))
+        R_want, t_want = Re @ R0, Re @ t0.astype(np.float64) + te.astype(np.float64)
+        # Eigen normalises nothing: the product carries the (1 + 1e-5) norm of the YAML quaternion; compare directions
+        R_got = replay.rotation_from_quat(q2.astype(np.float64) / np.linalg.norm(q2.astype(np.float64)))
+        assert abs(np.linalg.norm(q2.astype(np.float64)) - np.linalg.norm(qe.astype(np.float64))) < 1e-6
+        assert np.abs(R_got - R_want).max() < 5e-6, np.abs(R_got - R_want).max()
+        assert np.abs(t2 - t_want).max() < 5e-6
+        moved = max(moved, np.abs(t2 - t0).max())
+    assert moved > 0.01  # the offset of a few centimetres really is applied
+    # frames carry the composed pose
+    f = next(replay.read_log(str(tmp_path), cfg.depth_factor, L515_EXTRINSICS))
+    assert np.array_equal(f["q"], ext[0][1]) and np.array_equal(f["t"], ext[0][2])
+
+
 def test_tsdf_dump_records(tmp_path):
     cfg = synth.config("tiny")
     f = synth.Scene(cfg).frame(0)

@@ -10,7 +10,7 @@
 // for as long as the result stays in the binade: mantissa field <= 0x7FFFFF when the magnitude grows (the exact sum is
 // then below 2^(e+1), where the grid is still U -- and 2^(e+1) itself is representable on both grids), and >= 1 when
 // it shrinks (the exact sum is then above 2^e; below it the grid would be U / 2).  Steps that cross a binade, zeros,
-// denormals, infinities and NaN are simply taken for real.  tests/test_float_advance.py checks this file against plain
+// denormals, infinities and NaN are simply taken for real.  tools/experiments/float_advance_check.cc checks this file against plain
 // repeated addition on the CPU (random and adversarial operands).
 // STATUS: verified but NOT used by the kernels.  Wired into raycast_kernel together with a coarse far-field distance
 // map (skips of 64+ samples) it was bit-exact on the whole GPU parity suite and SLOWER (172.5 / 174.8 us per view against

@@ -1,10 +1,10 @@
-// CPU check of disinfect_slam_b200/csrc/float_advance.h against plain repeated float32 addition.
+// CPU check of tools/experiments/float_advance.h against plain repeated float32 addition.
 // Build: g++ -O2 -ffp-contract=off -msse2 -mfpmath=sse.  Prints "ok <cases>" or the first mismatch.
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <initializer_list>
-#include "../../disinfect_slam_b200/csrc/float_advance.h"
+#include "float_advance.h"
 
 static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
 static uint32_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return (uint32_t)(rng_state >> 16); }
