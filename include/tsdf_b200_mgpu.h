@@ -91,6 +91,20 @@ int tsdf_mgpu_gather(tsdf_mgpu_handle h, int root, const float* bbox /* 6 floats
  * on the engines / VoxelHashTable::NumActiveBlock of the whole volume. */
 int tsdf_mgpu_counters(tsdf_mgpu_handle h, tsdf_counters* last_frame_sum, tsdf_counters* totals_sum, int64_t* n_active_blocks);
 
+/* A whole stream of frames in one call -- the per-frame loop in C++, nothing but this library and NCCL between the
+ * frames.  For i in [first, first + count): frame = frames[i % n_frames]; tsdf_mgpu_integrate(frame), then
+ * raycast_mode 1: tsdf_mgpu_raycast from the frame's camera, 2: tsdf_mgpu_raycast_composite, 0: no view.
+ * Every rank passes the same cameras; plane pointers are read on `root` only.  Returns after enqueueing (the host only
+ * ever waits for the frame two steps back, which bounds the pipeline depth). */
+typedef struct tsdf_mgpu_frame {
+  const void *rgb, *depth, *ht, *lt; /* root only; host or device memory according to planes_on_device */
+  float q_xyzw[4];
+  float t_xyz[3];
+  float reserved;
+} tsdf_mgpu_frame;
+int tsdf_mgpu_run_sequence(tsdf_mgpu_handle h, int root, int planes_on_device, const tsdf_mgpu_frame* frames, int n_frames,
+                           int first, int count, int width, int height, float max_depth, const float K[4], int raycast_mode);
+
 /* Waits for everything this rank has enqueued (engine and communication streams). */
 int tsdf_mgpu_synchronize(tsdf_mgpu_handle h);
 

@@ -9,8 +9,8 @@ from disinfect_slam_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "tsdf_b200.h")).read()
+def declared_functions(header="tsdf_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(tsdf_[a-z_0-9]+)\s*\(", src)))
 
@@ -54,3 +54,19 @@ def test_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_multi_gpu_data_plane_header_and_binding_agree(tsdf_lib):
+    """libtsdf_b200_mgpu.so (NCCL linked directly) loads without a GPU and exports every symbol of
+    include/tsdf_b200_mgpu.h; it links NCCL and the engine, not torch."""
+    import subprocess
+    from disinfect_slam_b200 import mgpu
+    L = mgpu.lib()
+    names = declared_functions("tsdf_b200_mgpu.h")
+    assert sorted(mgpu.SYMBOLS) == names and len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), f"libtsdf_b200_mgpu.so does not export {n}"
+    assert C.sizeof(mgpu.Frame) == 64
+    needed = subprocess.run(["readelf", "-d", mgpu.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl.so" in needed and "libtsdf_b200.so" in needed and "torch" not in needed
+    assert L.tsdf_mgpu_destroy(None) == 0
