@@ -57,6 +57,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded single-stream leg at N > 1")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs 1, 3, 4, 5 legs")
+    ap.add_argument("--config1-frames", type=int, default=100)
+    ap.add_argument("--rooms", type=int, default=0, help="config 3: rooms of the synthetic floor (each = one lap of the config-2 frames); 0 = as many as ~50 M active voxels take")
+    ap.add_argument("--views", type=int, default=16, help="config 4: 1920x1080 virtual views per batch")
     ap.add_argument("--scale", type=float, default=1.0, help="image scale (debug only; 1.0 = the named config)")
     ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off"],
                     help="host waits of the e2e leg yield the CPU (TSDF_FLAG_BLOCKING_SYNC); auto = when the engine threads of all ranks reach half of the cores")
@@ -193,13 +197,19 @@ def run_reference(args, cfg, rank, world):
     sm_100a with its Release flags -> oracle/_ref/libref_tsdf.so) on this box's GPU 0, through its public
     Integrate / RayCast API, same streams-per-GPU workload as the own arm.  Fallback (library absent): the CPU
     oracle port on the host cores."""
-    if rank != 0:
-        return
     from oracle import ref_cuda
     if ref_cuda.available(parity=False):
+        # one replica set per GPU, like the own arm: every rank pins itself to its GPU BEFORE CUDA is initialised (the
+        # reference's TSDFGrid knows nothing about devices: it runs on device 0 of the process)
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        ids = vis.split(",") if vis else None
+        os.environ["CUDA_VISIBLE_DEVICES"] = ids[local_rank] if ids and local_rank < len(ids) else str(local_rank)
         import torch
         if torch.cuda.is_available():
-            return run_reference_cuda(args, cfg)
+            return run_reference_cuda(args, cfg, rank, world)
+    if rank != 0:
+        return
     from oracle.oracle import Oracle
     n_frames = min(args.lap, args.warmup + args.steps)
     st = generate_streams(cfg, 0, 1, n_frames)[0]
@@ -224,11 +234,15 @@ def run_reference(args, cfg, rank, world):
     emit(line)
 
 
-def run_reference_cuda(args, cfg):
+def run_reference_cuda(args, cfg, rank=0, world=1):
     from oracle.ref_cuda import RefTSDFGrid
     B, K, W = args.streams, args.steps, args.warmup
     n_frames = min(args.lap, W + K)
-    streams = generate_streams(cfg, 0, B, n_frames)
+    streams = generate_streams(cfg, rank, B, n_frames)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")  # plumbing: one barrier and one MAX of the wall time
     grids = [RefTSDFGrid(cfg.voxel_size, cfg.truncation, parity=False) for _ in range(B)]
     H, Wd = cfg.height, cfg.width
     npx = H * Wd
@@ -252,108 +266,52 @@ def run_reference_cuda(args, cfg):
     ths = [threading.Thread(target=worker, args=(b,)) for b in range(B)]
     for t in ths:
         t.start()
+    if dist is not None:
+        dist.barrier()
     start.wait()
     t0 = time.perf_counter()
     for t in ths:
         t.join()
     dt = time.perf_counter() - t0
     act = [g.num_active() for g in grids]
-    v = B * K / dt
-    desc = (f"the reference's own CUDA TSDFGrid (utils/tsdf/*.cu unmodified, -O3 -DNDEBUG, sm_100a) on GPU 0 of this box: {B} streams, "
-            f"one host thread each, TSDFGrid::Integrate(host cv::Mat planes) + TSDFGrid::RayCast + download of both images per frame; "
-            f"{K} timed steps after {W} warm-up; active blocks at end {act}")
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dt], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        dist.barrier()
+    if rank != 0:
+        for g in grids:
+            g.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    v = world * B * K / dt
+    desc = (f"the reference's own CUDA TSDFGrid (utils/tsdf/*.cu unmodified, -O3 -DNDEBUG, sm_100a), one replica set per GPU on {world} GPU(s) of this box: "
+            f"{B} streams per GPU, one host thread each, TSDFGrid::Integrate(host cv::Mat planes) + TSDFGrid::RayCast + download of both images per frame; "
+            f"{K} timed steps after {W} warm-up, wall time = max over ranks; active blocks at end (rank 0) {act}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(cfg, B, f"{B} independent streams interleaved per GPU, one frame of each per step"), frames_per_step=B),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": B, "kind": "reference", "sample": desc},
+            "config": workload_config(cfg, B, f"{B} independent streams interleaved per GPU, one frame of each per step", world),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": B * world, "kind": "reference", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 15 * npx * B, "d2h_bytes_per_step": 8 * npx * B},
             "gpu_launches": 0,
             "note": "the reference has no CPU TSDF path: this arm runs its CUDA kernels (oracle/_ref) on one B200; pageable host buffers as in its API"}
     emit(line)
     for g in grids:
         g.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
-def workload_config(cfg, streams, extra):
+def workload_config(cfg, streams, extra, world=1):
+    """Identical for the own arm and the reference arm (the driver compares the two)."""
     return {"workload": f"{cfg.name}: Integrate + RayCast every frame; {extra}", "width": cfg.width, "height": cfg.height,
             "voxel_size_m": cfg.voxel_size, "truncation_m": cfg.truncation, "max_depth_m": cfg.max_depth,
-            "block": "8^3 voxels", "streams_per_gpu": streams, "pool_blocks": cfg.pool_blocks}
-
-
-# --------------------------------------------------------------------------------------------------
-# sharded single-stream leg (N > 1): block-coordinate ownership, NCCL frame broadcast, min-composited RayCast
-# --------------------------------------------------------------------------------------------------
-def sharded_leg(args, cfg, st, d0, rank, world, local_rank, dev, n_frames, W, K):
-    import torch
-    import torch.distributed as dist
-    from disinfect_slam_b200 import sharded, tsdf_grid
-    H, Wd = cfg.height, cfg.width
-    n = H * Wd
-    # camera of every frame of rank 0's stream 0, shared once up front
-    cams = torch.zeros((n_frames, 7), dtype=torch.float32, device=dev)
-    if rank == 0:
-        cams.copy_(torch.from_numpy(np.concatenate([np.stack(st["q"]), np.stack(st["t"])], 1).astype(np.float32)))
-    Kt = torch.tensor(np.asarray(st["K"], np.float32) if rank == 0 else np.zeros(4, np.float32), device=dev)
-    dist.broadcast(cams, src=0)
-    dist.broadcast(Kt, src=0)
-    cams, Kv = cams.cpu().numpy(), Kt.cpu().numpy()
-    cam = tsdf_grid.CameraParams(Kv, H, Wd)
-    # packed [depth | ht | lt | rgb] frames, resident on the root; receive buffers elsewhere
-    if rank == 0:
-        packed = [torch.cat([d0["depth"][i].reshape(-1).view(torch.uint8), d0["ht"][i].reshape(-1).view(torch.uint8),
-                             d0["lt"][i].reshape(-1).view(torch.uint8), d0["rgb"][i].reshape(-1)]) for i in range(n_frames)]
-    else:
-        packed = [torch.empty(15 * n, dtype=torch.uint8, device=dev) for _ in range(3)]
-    g = sharded.ShardedTSDFGrid(cfg.voxel_size, cfg.truncation, device=local_rank, shard_shift=2, pool_blocks=cfg.pool_blocks,
-                                table_slots=cfg.table_slots, max_image_pixels=n)
-
-    def step(i, exact):
-        fi = i % n_frames
-        buf = packed[fi] if rank == 0 else packed[i % 3]
-        q, t = cams[fi, :4], cams[fi, 4:]
-        g.IntegrateBroadcast(buf, Wd, H, cfg.max_depth, Kv, q, t)
-        if exact:
-            return g.RayCastExact(cfg.max_depth, cam, (q, t), to_host=False)[2]
-        return g.RayCastKeys(cfg.max_depth, cam, (q, t))
-
-    def timed(exact):
-        for i in range(W):
-            step(i, exact)
-        g.synchronize()
-        g.backend.grid.set_profiling(False)
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(W, W + K):
-            last = step(i, exact)
-        g.synchronize()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        return float(dt.item()), last
-
-    # two laps over the same frames: first with the exact RayCast (peer memory over NVLink, rows split across the
-    # ranks), then -- on the volume that now exists -- with the min-composited one
-    dt_exact, depth = timed(True)
-    tot = g.backend.grid.totals()
-    hits = int(torch.isfinite(depth).sum().item())
-    dt_comp, _ = timed(False)
-    cnt = torch.tensor([tot["n_updated"], tot["n_visible"], g.backend.num_active()], device=dev, dtype=torch.int64)
-    allc = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(allc, cnt)
-    g.close()
-    upd = sum(int(c[0]) for c in allc)
-    rows = (H + world - 1) // world
-    return {"frames_per_s": K / dt_exact, "ms_per_frame": 1e3 * dt_exact / K, "voxel_updates_per_s": upd / dt_exact,
-            "raycast_mrays_per_s": K * n / dt_exact / 1e6, "raycast": "exact: tsdf_raycast_shared, each rank marches 1/N of the rows over the whole volume",
-            "active_blocks_per_rank": [int(c[2]) for c in allc], "visible_blocks_per_rank_per_frame": [int(c[1]) / K for c in allc],
-            "last_view_hit_fraction": hits / n, "shard_shift": 2,
-            "collectives_per_frame": f"1 NCCL broadcast of {15 * n} B, a 4-byte all-reduce (device-side barrier), 3 all-gathers of {rows * Wd * 4} / {rows * Wd * 4} / {rows * Wd * 4} B per rank",
-            "min_composite_variant": {"frames_per_s": K / dt_comp, "ms_per_frame": 1e3 * dt_comp / K,
-                                      "collectives_per_frame": f"1 NCCL broadcast of {15 * n} B + 1 all-reduce(MIN) of {16 * n} B",
-                                      "note": "second lap over the same frames (volume already built); inexact at shard boundaries"},
-            "timing": "host clock around K frames bracketed by synchronize + barrier, max over ranks (engine and NCCL work are stream-ordered, no host sync inside)"}
+            "block": "8^3 voxels", "streams_per_gpu": streams, "pool_blocks": cfg.pool_blocks,
+            "frames_per_step": streams * world, "parallelism": f"replicas x{world} (independent streams, no data-path collective)",
+            "l2": "inputs larger than L2: the streams of a GPU are interleaved so that the per-step working set (visible voxel blocks + frame "
+                  "planes of all streams, ~400 MB with 4 streams) exceeds the 126 MB L2; no explicit flush"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -387,6 +345,10 @@ def main():
     B, K, W = args.streams, args.steps, args.warmup
     n_frames = min(args.lap, W + K)
     streams = generate_streams(cfg, rank, B, n_frames)  # before CUDA init (fork)
+    # BASELINE configs[0] / configs[4]: one 640x480 stream per GPU (its own seed per rank)
+    cfg1 = synth.config("config1")
+    n1 = 0 if args.no_extra_configs else min(cfg1.n_frames, args.config1_frames)
+    stream1 = generate_streams(replace(cfg1, seed=cfg1.seed + 31 * rank), 0, 1, n1)[0] if n1 else None
 
     import torch
     import torch.distributed as dist
@@ -659,10 +621,31 @@ def main():
             del hp_in, hp_out, d_in, d_out
         except Exception as ex:  # supplementary only
             e2e["pcie_measured_gbs"] = {"error": repr(ex)}
-    # ---------------- leg 4 (N > 1): ONE stream whose volume is sharded over all ranks ----------------
-    shard = None
-    if world > 1 and not args.no_sharded:
-        shard = sharded_leg(args, cfg, streams[0], dres[0], rank, world, local_rank, dev, n_frames, W, K)
+    # ---------------- BASELINE configs 1, 3, 4, 5 (bench_legs.py) ----------------
+    # config 3 at N > 1 is the sharded measurement: ONE stream whose volume is sharded over all ranks through the
+    # C++ / NCCL data plane; at N = 1 the same stream runs on the plain engine
+    extra = {}
+    if not args.no_extra_configs:
+        import bench_legs
+        try:
+            if not (world > 1 and args.no_sharded):
+                extra["config3"], extra["config4"] = bench_legs.config3_and_4(args, cfg, streams[0], dres[0], rank, world, local_rank, dev, n_frames, W, K,
+                                                                            dist if world > 1 else None)
+        except Exception as ex:  # supplementary legs never lose the headline line
+            import traceback
+            extra["config3"] = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
+        try:
+            if stream1 is not None:
+                extra["config1"], extra["config5"] = bench_legs.config1_and_5(args, stream1, rank, world, local_rank, dev, dist if world > 1 else None)
+        except Exception as ex:
+            import traceback
+            extra["config1"] = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
+    # exact voxel-update count of the headline leg: summed over the ranks, not extrapolated
+    upd_all = upd_local
+    if world > 1:
+        tt = torch.tensor([upd_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(tt)
+        upd_all = int(tt.item())
     sampler.stop()
 
     if rank != 0:
@@ -673,7 +656,6 @@ def main():
     # ---------------- numbers ----------------
     frames = world * B * K
     value = frames / (ms * 1e-3)
-    upd_all = upd_local * world  # ranks run statistically identical streams; exact per-rank sums are rank-local
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -699,9 +681,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(cfg, B, f"{B} independent streams interleaved per GPU, one frame of each per step"),
-                       frames_per_step=B * world, parallelism=f"replicas x{world} (independent streams, no data-path collective)",
-                       l2=f"inputs larger than L2: per-step working set {ws / 1e6:.0f} MB (visible voxel blocks + frame planes of {B} streams) vs 126 MB L2; no explicit flush"),
+        "config": workload_config(cfg, B, f"{B} independent streams interleaved per GPU, one frame of each per step", world),
+        "working_set_mb_per_step": ws / 1e6,
         "voxel_updates_per_s": upd_all / (ms * 1e-3),
         "voxel_updates_per_frame": n_upd / max(tot["frames"], 1),
         "raycast_mrays_per_s": frames * npx / (ms * 1e-3) / 1e6,
@@ -722,8 +703,7 @@ def main():
         "clocks": sampler.summary(windows[:1]),
         "counters_per_frame": {k: tot[k] / max(tot["frames"], 1) for k in ("n_new", "n_visible", "n_updated", "n_carved", "n_active_post")},
     }
-    if shard is not None:
-        line["sharded_single_stream"] = shard
+    line["configs"] = extra
     if not args.no_cpu_baseline and world == 1:
         v, n, dt = cpu_sample(cfg, streams[0], args.cpu_seconds, n_frames)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": oracle_threads(), "kind": "port",

@@ -8,9 +8,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <vector>
 
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include "../../include/tsdf_b200.h"
@@ -73,6 +76,8 @@ struct tsdf_engine {
   float* mesh_out = nullptr; size_t mesh_cap = 0; int64_t mesh_n = 0;  // triangles (9 floats each), grow-only
   unsigned long long* mesh_counter = nullptr;
   int* h_scalar = nullptr;  // pinned scratch (C_COUNT ints)
+  unsigned char* bounce[2] = {nullptr, nullptr};  // pinned staging for large device -> pageable-host results (see copy_to_host)
+  cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
   int n_active = 0;         // host mirror after the last completed frame
   tsdf_counters last{};
   bool profiling = false;
@@ -262,7 +267,7 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
     if (user_cfg->struct_size != (int32_t)sizeof(tsdf_config)) return fail(TSDF_E_INVALID, "tsdf_config.struct_size mismatch");
     cfg = *user_cfg;
   }
-  if (cfg.pool_blocks <= 0 || cfg.table_slots <= 0 || (cfg.table_slots & (cfg.table_slots - 1)))
+  if (cfg.pool_blocks <= 0 || cfg.pool_blocks >= (1 << kIndexShardShift) || cfg.table_slots <= 0 || (cfg.table_slots & (cfg.table_slots - 1)))
     return fail(TSDF_E_INVALID, "pool_blocks must be > 0 and table_slots a power of two");
   if (cfg.table_slots < 2 * (int64_t)cfg.pool_blocks) return fail(TSDF_E_INVALID, "table_slots must be >= 2 * pool_blocks");
   if (cfg.shard_count < 1 || cfg.shard_rank < 0 || cfg.shard_rank >= cfg.shard_count)
@@ -348,6 +353,7 @@ int tsdf_destroy(tsdf_handle e) {
   }
   cudaFree(e->rgba); cudaFree(e->normal); cudaFree(e->hit_depth); cudaFree(e->gather_out);
   if (e->h_scalar) cudaFreeHost(e->h_scalar);
+  for (int i = 0; i < 2; ++i) { if (e->bounce[i]) cudaFreeHost(e->bounce[i]); if (e->bounce_ev[i]) cudaEventDestroy(e->bounce_ev[i]); }
   if (e->ev_block) cudaEventDestroy(e->ev_block);
   phase_collect(e);
   for (cudaEvent_t v : e->ev_pool) cudaEventDestroy(v);
@@ -603,20 +609,106 @@ int tsdf_peer_attach_local(tsdf_handle e, int world, const tsdf_handle* shards) 
   return TSDF_OK;
 }
 
-int tsdf_raycast_shared(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
-                        int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth) {
+static int raycast_shared_impl(tsdf_engine* e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                               int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth, int n_out, void* const* out_rgba,
+                               void* const* out_normal, void* const* out_depth) {
   if (!e || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
   if (e->n_peers < 1) return fail(TSDF_E_INVALID, "no peers attached (tsdf_ipc_attach / tsdf_peer_attach_local)");
   if (w <= 0 || h <= 0 || row0 < 0 || rows < 0) return fail(TSDF_E_INVALID, "bad image size / row range");
+  if (n_out < 0 || n_out > kMaxPeers) return fail(TSDF_E_INVALID, "at most %d destinations", kMaxPeers);
   CU(cudaSetDevice(e->device));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
   phase_begin(e, PH_RAYCAST, e->stream);
-  launch_build_skip_map(e->d_peers, e->n_peers, e->skip, ++e->skip_gen, false, e->num_sms, e->stream);  // union of every shard's blocks
-  e->skip_epoch = 0;  // the map no longer describes this engine alone
+  // union of every shard's blocks.  Other shards change without this host knowing, so the attempt is always launched;
+  // the kernels return at once when no shard's block set changed since the last build (device-side serials)
+  launch_build_skip_map(e->d_peers, e->n_peers, e->skip, ++e->skip_gen, true, e->num_sms, e->stream);
+  e->skip_epoch = 0;  // a local RayCast must look again: the map may describe more than this engine
   launch_raycast_shared(e->d_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0),
-                        (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, e->stream);
+                        (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, n_out, out_rgba, out_normal, out_depth, e->stream);
   phase_end(e, PH_RAYCAST, e->stream);
   CU(cudaGetLastError());
+  return TSDF_OK;
+}
+int tsdf_raycast_shared(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                        int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth) {
+  return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, d_rgba, d_normal, d_hit_depth, 0, nullptr, nullptr, nullptr);
+}
+int tsdf_raycast_shared_scatter(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                                int row0, int rows, int n_dest, void* const* d_rgba, void* const* d_normal, void* const* d_hit_depth) {
+  if (n_dest < 1) return fail(TSDF_E_INVALID, "need at least one destination");
+  return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, nullptr, nullptr, nullptr, n_dest, d_rgba, d_normal, d_hit_depth);
+}
+
+// Large results (GatherValid / GatherVoxels records, meshes) to host memory at PCIe speed.
+//  * pinned destination (tsdf_host_alloc, cudaHostRegister): one asynchronous copy -- the DMA engine writes the
+//    caller's memory directly;
+//  * pageable destination (the std::vector the reference's signatures return, a fresh numpy array): the copy is
+//    pipelined in 16 MB chunks through two engine-owned pinned buffers -- the DMA of chunk i+1 runs while four host
+//    threads move chunk i into the destination.  A fresh allocation is all page faults (expensive on a virtualised
+//    host), so every thread first asks the kernel to populate its part in one batch (MADV_POPULATE_WRITE; ignored
+//    where unsupported).  TSDF_PAGEABLE_COPY=driver selects the plain cudaMemcpy of the reference
+//    (voxel_tsdf.cu:420-422,449-451) instead.
+static int copy_to_host(tsdf_engine* e, void* dst, const void* d_src, size_t bytes) {
+  if (!bytes) return TSDF_OK;
+  cudaPointerAttributes at{};
+  const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  constexpr size_t kChunk = (size_t)16 << 20;
+  static const bool use_driver = [] { const char* v = getenv("TSDF_PAGEABLE_COPY"); return v && !strcmp(v, "driver"); }();
+  if (pinned || bytes <= kChunk / 4 || use_driver) {
+    CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(wait_stream(e, e->stream));
+    return TSDF_OK;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (!e->bounce[i]) { CU(cudaMallocHost(&e->bounce[i], kChunk)); CU(cudaEventCreateWithFlags(&e->bounce_ev[i], cudaEventDisableTiming)); }
+  }
+  const int n_chunks = (int)((bytes + kChunk - 1) / kChunk);
+  constexpr int kThreads = 4;
+  std::atomic<int> ready{0};               // chunks [0, ready) are in their bounce buffer
+  std::atomic<int> finished[2] = {{0}, {0}};  // helpers done with the chunk currently in bounce[p]
+  auto share = [&](int chunk, int t) {     // thread t's part of `chunk`: a contiguous quarter, page aligned
+    const size_t off = (size_t)chunk * kChunk, len = std::min(kChunk, bytes - off);
+    const size_t per = ((len / kThreads) + 4095) & ~(size_t)4095;
+    const size_t a = std::min(len, per * t), b = t == kThreads - 1 ? len : std::min(len, per * (t + 1));
+    if (b > a) {
+#ifdef MADV_POPULATE_WRITE
+      const uintptr_t lo = ((uintptr_t)dst + off + a + 4095) & ~(uintptr_t)4095, hi = ((uintptr_t)dst + off + b) & ~(uintptr_t)4095;
+      if (hi > lo) madvise((void*)lo, hi - lo, MADV_POPULATE_WRITE);  // batch the page faults of a fresh destination
+#endif
+      memcpy((char*)dst + off + a, e->bounce[chunk & 1] + a, b - a);
+    }
+  };
+  std::vector<std::thread> helpers;
+  for (int t = 1; t < kThreads; ++t)
+    helpers.emplace_back([&, t]() {
+      for (int c = 0; c < n_chunks; ++c) {
+        while (ready.load(std::memory_order_acquire) <= c) std::this_thread::yield();
+        share(c, t);
+        finished[c & 1].fetch_add(1, std::memory_order_release);
+      }
+    });
+  cudaError_t err = cudaSuccess;
+  auto issue = [&](int c) {
+    const size_t off = (size_t)c * kChunk, len = std::min(kChunk, bytes - off);
+    cudaError_t r = cudaMemcpyAsync(e->bounce[c & 1], (const char*)d_src + off, len, cudaMemcpyDeviceToHost, e->stream);
+    if (r == cudaSuccess) r = cudaEventRecord(e->bounce_ev[c & 1], e->stream);
+    if (r != cudaSuccess && err == cudaSuccess) err = r;
+  };
+  issue(0);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) {  // bounce[(c + 1) & 1] held chunk c - 1: every helper must be done with it
+      if (c >= 1) while (finished[(c + 1) & 1].load(std::memory_order_acquire) < (kThreads - 1) * ((c + 1) / 2)) std::this_thread::yield();
+      issue(c + 1);
+    }
+    const cudaError_t r = cudaEventSynchronize(e->bounce_ev[c & 1]);
+    if (r != cudaSuccess && err == cudaSuccess) err = r;
+    ready.store(c + 1, std::memory_order_release);
+    share(c, 0);
+  }
+  for (auto& h : helpers) h.join();
+  if (err != cudaSuccess) return fail(TSDF_E_CUDA, "device -> host copy failed: %s", cudaGetErrorString(err));
+  CU(wait_stream(e, e->stream));
   return TSDF_OK;
 }
 
@@ -658,7 +750,7 @@ static int gather_impl(tsdf_engine* e, const float* bbox, float* out, int64_t ca
   if (n_voxels) *n_voxels = e->gather_n;
   if (out && cap > 0) {
     const size_t m = (size_t)std::min<int64_t>(cap, e->gather_n);
-    if (m) CU(cudaMemcpyAsync(out, e->gather_out, sizeof(float4) * m, cudaMemcpyDeviceToHost, e->stream));
+    return copy_to_host(e, out, e->gather_out, sizeof(float4) * m);
   }
   CU(wait_stream(e, e->stream));
   return TSDF_OK;
@@ -672,9 +764,7 @@ int tsdf_gather_fetch(tsdf_handle e, float* out, int64_t cap) {
   if (!e || !out) return fail(TSDF_E_INVALID, "null argument");
   CU(cudaSetDevice(e->device));
   const size_t m = (size_t)std::min<int64_t>(cap, e->gather_n);
-  if (m) CU(cudaMemcpyAsync(out, e->gather_out, sizeof(float4) * m, cudaMemcpyDeviceToHost, e->stream));
-  CU(wait_stream(e, e->stream));
-  return TSDF_OK;
+  return copy_to_host(e, out, e->gather_out, sizeof(float4) * m);
 }
 int tsdf_gather_device_result(tsdf_handle e, const void** d_out, int64_t* n) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
@@ -716,7 +806,7 @@ int tsdf_extract_mesh(tsdf_handle e, const float* bbox, float* out, int64_t cap,
   if (n_triangles) *n_triangles = e->mesh_n;
   if (out && cap > 0) {
     const size_t m = (size_t)std::min<int64_t>(cap, e->mesh_n);
-    if (m) CU(cudaMemcpyAsync(out, e->mesh_out, sizeof(float) * 9 * m, cudaMemcpyDeviceToHost, e->stream));
+    return copy_to_host(e, out, e->mesh_out, sizeof(float) * 9 * m);
   }
   CU(wait_stream(e, e->stream));
   return TSDF_OK;
@@ -725,9 +815,7 @@ int tsdf_mesh_fetch(tsdf_handle e, float* out, int64_t cap) {
   if (!e || !out) return fail(TSDF_E_INVALID, "null argument");
   CU(cudaSetDevice(e->device));
   const size_t m = (size_t)std::min<int64_t>(cap, e->mesh_n);
-  if (m) CU(cudaMemcpyAsync(out, e->mesh_out, sizeof(float) * 9 * m, cudaMemcpyDeviceToHost, e->stream));
-  CU(wait_stream(e, e->stream));
-  return TSDF_OK;
+  return copy_to_host(e, out, e->mesh_out, sizeof(float) * 9 * m);
 }
 int tsdf_mesh_device_result(tsdf_handle e, const void** d_out, int64_t* n) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");

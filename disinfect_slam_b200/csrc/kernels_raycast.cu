@@ -28,19 +28,25 @@ namespace tsdf {
 // header from the AABB counters + fill with the cap.  Every thread derives the same header (a handful of integer
 // operations) so that no separate one-thread launch is needed; thread 0 publishes it for the later kernels.
 // Build attempts are numbered (gen) by the host.  With `lazy` set, attempt g first compares the serial of the last call
-// that changed the block set (ctr[C_DIRTY], written by table_insert / table_erase) with the one recorded by attempt
-// g - 1: equal means the map is still exact and all five kernels return at once -- a frame that neither allocated nor
-// carved a block (a static camera, a converged scene) costs five empty launches instead of a rebuild.  The two
-// records alternate between hdr[8] / hdr[9] so that no thread reads a word another thread of the same kernel writes;
-// the verdict for the four later kernels goes to hdr[10 + (g & 1)].
+// that changed each shard's block set (ctr[C_DIRTY], written on NET changes only, see mark_block_set_changed; read
+// over NVLink for foreign shards) with the serials recorded by attempt g - 1: all equal means the map is still exact
+// and all five kernels return at once -- a frame that neither allocated nor carved a surviving block (a static
+// camera, a converged scene), or a batch of views over a finished volume, costs five empty launches instead of a
+// rebuild.  The records of consecutive attempts alternate between two halves of the header, so that no thread reads
+// a word another thread of the same kernel writes; the verdict for the four later kernels goes to hdr[10 + (g & 1)].
 __global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M, int gen, int lazy) {
-  if (lazy) {
-    const int serial = shards[0].ctr[C_DIRTY];
-    const bool rebuild = M.hdr[8 + ((gen - 1) & 1)] != serial;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { M.hdr[8 + (gen & 1)] = serial; M.hdr[10 + (gen & 1)] = rebuild ? 1 : 0; if (rebuild) M.hdr[12]++; }
+  {
+    int* const now = M.hdr + kSkipSigBase + (gen & 1) * kSkipSigInts;
+    const int* const before = M.hdr + kSkipSigBase + ((gen - 1) & 1) * kSkipSigInts;
+    bool rebuild = !lazy || before[0] != n_shards;
+    for (int r = 0; r < n_shards; ++r) rebuild = rebuild || before[1 + r] != shards[r].ctr[C_DIRTY];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      now[0] = n_shards;
+      for (int r = 0; r < n_shards; ++r) now[1 + r] = shards[r].ctr[C_DIRTY];
+      M.hdr[10 + (gen & 1)] = rebuild ? 1 : 0;
+      if (rebuild) M.hdr[12]++;
+    }
     if (!rebuild) return;
-  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
-    M.hdr[8 + (gen & 1)] = -1; M.hdr[10 + (gen & 1)] = 1; M.hdr[12]++;  // -1 never equals a serial: the next lazy attempt rebuilds
   }
   // AABB of every shard's inserts (one shard = the engine itself; several = a volume sharded over GPUs, whose
   // counters are read over NVLink)
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restri
   const uint4 cap16 = make_uint4(0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 15) / 16; i += gridDim.x * blockDim.x)
     reinterpret_cast<uint4*>(M.dist)[i] = cap16;
-  if (shift == 0 && n_shards == 1) {  // one cell = one block of one engine: a dense block index beside the distances
+  if (shift == 0) {  // one cell = one block: a dense block index (owner shard << kIndexShardShift | pool index) beside the distances
     const int4 none = make_int4(-1, -1, -1, -1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 3) / 4; i += gridDim.x * blockDim.x)
       reinterpret_cast<int4*>(M.index)[i] = none;
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restri
       const int cx = (bx - ox) >> shift, cy = (by - oy) >> shift, cz = (bz - oz) >> shift;
       const size_t cell = ((size_t)cz * ny + cy) * nx + cx;
       M.dist[cell] = 0;
-      if (shift == 0 && n_shards == 1) M.index[cell] = i;  // directory position = pool index
+      if (shift == 0) M.index[cell] = (r << kIndexShardShift) | i;  // directory position = pool index
     }
   }
 }
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigne
 }
 
 void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int gen, bool lazy, int num_sms, cudaStream_t st) {
-  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(shards, n_shards, M, gen, lazy && n_shards == 1 ? 1 : 0);
+  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(shards, n_shards, M, gen, lazy ? 1 : 0);
   skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(shards, n_shards, M, gen);
   skip_pass_kernel<0><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, gen);
   skip_pass_kernel<1><<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist, gen);
@@ -145,9 +151,15 @@ template <> struct Volume<false> {
   }
 };
 template <> struct Volume<true> {
-  static constexpr bool kDenseIndex = false;
+  static constexpr bool kDenseIndex = true;
   const PeerView* shards; int n_shards, shard_shift;
-  __device__ __forceinline__ const unsigned char* at(int) const { return nullptr; }
+  // Fused exchange of the results: when n_out > 0 every ray's pixel is stored into the image buffers of ALL ranks
+  // (peer-mapped pointers, posted stores over NVLink issued as the rays finish) instead of into one local image that an
+  // all-gather would have to distribute afterwards.
+  int n_out; uchar4* out_rgba[kMaxPeers]; uchar4* out_normal[kMaxPeers]; float* out_depth[kMaxPeers];
+  __device__ __forceinline__ const unsigned char* at(int idx) const {  // owner shard in the top bits: no table probe over NVLink
+    return idx < 0 ? nullptr : shards[idx >> kIndexShardShift].voxels + (size_t)(idx & ((1 << kIndexShardShift) - 1)) * kBlockBytes;
+  }
   __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
     const u64 key = pack_key(bx, by, bz);
     const PeerView& v = shards[owner_of(key, n_shards, shard_shift)];
@@ -395,6 +407,16 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
     out_depth = pc.z;
   }
 
+  if constexpr (SHARED) {
+    if (vol.n_out > 0) {
+      for (int r = 0; r < vol.n_out; ++r) {
+        if (vol.out_rgba[r]) reinterpret_cast<uint32_t*>(vol.out_rgba[r])[idx] = out_rgba;
+        if (vol.out_normal[r]) reinterpret_cast<uint32_t*>(vol.out_normal[r])[idx] = out_normal;
+        if (vol.out_depth[r]) vol.out_depth[r][idx] = out_depth;
+      }
+      return;
+    }
+  }
   if (img_rgba) reinterpret_cast<uint32_t*>(img_rgba)[idx] = out_rgba;
   if (img_normal) reinterpret_cast<uint32_t*>(img_normal)[idx] = out_normal;
   if (img_depth) img_depth[idx] = out_depth;
@@ -429,12 +451,18 @@ void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size,
 // from their owner over NVLink.
 void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
                            const SkipMap& M, int row0, int rows, uchar4* rgba, uchar4* normal, float* hit_depth,
-                           cudaStream_t st) {
+                           int n_out, void* const* out_rgba, void* const* out_normal, void* const* out_depth, cudaStream_t st) {
   if (rows <= 0) return;
   dim3 grid((P.w + 31) / 32, (rows + 7) / 8);
   SkipMap R = M;
   R.dist = M.scratch; R.scratch = M.dist;
   Volume<true> vol; vol.shards = shards; vol.n_shards = n_shards; vol.shard_shift = shard_shift;
+  vol.n_out = n_out;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    vol.out_rgba[r] = r < n_out && out_rgba ? (uchar4*)out_rgba[r] : nullptr;
+    vol.out_normal[r] = r < n_out && out_normal ? (uchar4*)out_normal[r] : nullptr;
+    vol.out_depth[r] = r < n_out && out_depth ? (float*)out_depth[r] : nullptr;
+  }
   if (view_needs_clamp(P, step_size)) raycast_kernel<true, true><<<grid, 256, 0, st>>>(vol, P, step_size, R, row0, rows, rgba, normal, hit_depth, nullptr);
   else raycast_kernel<true, false><<<grid, 256, 0, st>>>(vol, P, step_size, R, row0, rows, rgba, normal, hit_depth, nullptr);
 }

@@ -8,11 +8,14 @@
 //
 //   stream `cs` (communication)   frame k+1: [root: H2D of the planes] -> grouped ncclBroadcast (comm_frame)
 //   stream `es` (engine)          frame k: allocate / select / integrate of the owned blocks
-//                                 view k:  4-byte ncclAllReduce (barrier) -> skip map over all shards + march of this
-//                                          rank's rows with peer loads over NVLink -> grouped in-place ncclAllGather
-//                                          (comm_sync)
-// Two communicators, because the broadcast of the next frame runs concurrently with the barrier / all-gather of the
-// current view; every rank issues the calls in the same order.
+//                                 view k:  peer barrier -> skip map over all shards + march of this rank's rows with
+//                                          peer loads over NVLink, every finished ray stored straight into the image
+//                                          buffers of ALL ranks (posted NVLink stores) -> peer barrier
+// The peer barrier is one 32-thread kernel: a release-store of the epoch into a flag word of every peer and an
+// acquire-spin on the own flag words -- no NCCL kernel on the engine stream at all (TSDF_MGPU_EXCHANGE=nccl selects
+// the conventional form instead: 4-byte ncclAllReduce, local image, grouped in-place ncclAllGather on comm_sync).
+// Two communicators, because the broadcast of the next frame runs concurrently with collectives of the current view;
+// every rank issues its calls in the same order.
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -20,6 +23,7 @@
 
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include "../../include/tsdf_b200_mgpu.h"
 
@@ -47,6 +51,9 @@ int fail(int code, const char* fmt, ...) {
     if (r_ != TSDF_OK) return fail(r_, "%s: %s", #call, tsdf_last_error());                                    \
   } while (0)
 
+constexpr int kMaxRanks = 8;
+constexpr size_t kFlagBytes = 256;
+constexpr size_t kRowSlack = (size_t)kMaxRanks * 8192;  // pixels: the in-place all-gather pads the image to world * rows_per rows
 constexpr int kStage = 3;  // frame staging sets: broadcast of frame k+1 while frame k integrates and k-1 retires
 enum { T_BCAST = 0, T_BARRIER, T_ALLGATHER, T_COMPOSITE, T_RAYCAST, T_GATHER, T_COUNT };
 
@@ -67,9 +74,15 @@ struct tsdf_mgpu {
   Stage stage[kStage];
   int cur = 0;
   int* d_flag = nullptr;
-  // assembled images: world * rows_per * width pixels each, so that every rank's rows form one equal-sized chunk
+  // exchange buffer of this rank, mapped by every peer: [rgba | normal | hit depth] images of (max_px + slack) pixels
+  // each, then the barrier flag words (one per peer)
+  unsigned char* xbuf = nullptr; size_t img_stride = 0;
+  unsigned char* xpeer[kMaxRanks] = {};     // every rank's exchange buffer as seen from this GPU ([rank] = xbuf)
+  void* xopened[kMaxRanks] = {};            // cudaIpcOpenMemHandle results (closed at destroy)
   unsigned char* img[3] = {nullptr, nullptr, nullptr};
-  size_t img_cap_px = 0;
+  int epoch = 0;                            // barrier count (identical on all ranks: same call sequence)
+  int* d_err = nullptr;                     // set by a barrier that timed out
+  bool fused = true;
   int last_w = 0, last_h = 0;
   unsigned long long* keys = nullptr; size_t keys_cap = 0;
   long long* d_sizes = nullptr; long long* h_sizes = nullptr;  // [world] gather sizes / counter sums
@@ -107,6 +120,28 @@ void collect(tsdf_mgpu* m) {
   }
 }
 int rows_per_rank(const tsdf_mgpu* m, int h) { return (h + m->world - 1) / m->world; }
+
+// Barrier over the GPUs of the volume without a collective library: lane r publishes this rank's arrival at `epoch` in
+// peer r's flag word [rank] (release store at system scope, after a system fence: everything earlier kernels of this
+// stream wrote -- voxels, image rows stored into peer buffers -- is visible to whoever acquires the flag), then waits
+// until peer r's arrival shows up in the own flag word [r].  Epochs only grow, a fast peer may already be one ahead.
+struct PeerFlags { int* flags[kMaxRanks]; };
+__global__ void peer_barrier_kernel(PeerFlags peers, int rank, int world, int epoch, long long timeout_cycles, int* err) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.flags[r] + rank), "r"(epoch) : "memory");
+  const int* mine = peers.flags[rank] + r;
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v - epoch >= 0) break;
+    if (clock64() - t0 > timeout_cycles) { *err = epoch; break; }  // a peer died: report instead of hanging the GPU
+  }
+}
+
+struct XBlob { cudaIpcMemHandle_t h; long long pid; void* raw; int device; int pad; };
 }  // namespace
 
 extern "C" {
@@ -134,7 +169,8 @@ int tsdf_mgpu_destroy(tsdf_mgpu_handle m) {
     if (s.received) cudaEventDestroy(s.received);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
-  for (unsigned char* p : m->img) cudaFree(p);
+  for (int r = 0; r < kMaxRanks; ++r) if (m->xopened[r]) cudaIpcCloseMemHandle(m->xopened[r]);
+  cudaFree(m->xbuf); cudaFree(m->d_err);
   cudaFree(m->d_flag); cudaFree(m->keys); cudaFree(m->d_sizes); cudaFree(m->gather_all);
   if (m->h_sizes) cudaFreeHost(m->h_sizes);
   collect(m);
@@ -202,6 +238,46 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
     CU(cudaStreamSynchronize(m->es));
     cudaFree(d_blobs);
     TS(tsdf_ipc_attach(m->eng, world, blobs.data()));
+    // exchange buffer (images + barrier flags) of every rank, mapped the same way
+    m->img_stride = 4 * (m->max_px + kRowSlack);
+    CU(cudaMalloc(&m->xbuf, 3 * m->img_stride + kFlagBytes));
+    CU(cudaMemsetAsync(m->xbuf, 0, 3 * m->img_stride + kFlagBytes, m->es));
+    CU(cudaMalloc(&m->d_err, sizeof(int)));
+    CU(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->es));
+    for (int i = 0; i < 3; ++i) m->img[i] = m->xbuf + (size_t)i * m->img_stride;
+    {
+      const char* ex = getenv("TSDF_MGPU_EXCHANGE");
+      m->fused = !(ex && !strcmp(ex, "nccl"));
+      std::vector<XBlob> xb(world);
+      XBlob mine{};
+      CU(cudaIpcGetMemHandle(&mine.h, m->xbuf));
+      mine.pid = (long long)getpid(); mine.raw = m->xbuf; mine.device = m->device;
+      XBlob* d_xb = nullptr;
+      CU(cudaMalloc(&d_xb, sizeof(XBlob) * world));
+      CU(cudaMemcpyAsync(d_xb + rank, &mine, sizeof(XBlob), cudaMemcpyHostToDevice, m->es));
+      NC(ncclAllGather(d_xb + rank, d_xb, sizeof(XBlob), ncclChar, m->comm_sync, m->es));
+      CU(cudaMemcpyAsync(xb.data(), d_xb, sizeof(XBlob) * world, cudaMemcpyDeviceToHost, m->es));
+      CU(cudaStreamSynchronize(m->es));
+      cudaFree(d_xb);
+      for (int r = 0; r < world; ++r) {
+        if (r == rank) { m->xpeer[r] = m->xbuf; continue; }
+        if (xb[r].pid == (long long)getpid()) {  // a rank of this process (thread per GPU): plain peer access
+          if (xb[r].device != m->device) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(xb[r].device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(TSDF_E_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", xb[r].device, cudaGetErrorString(pe));
+            cudaGetLastError();
+          }
+          m->xpeer[r] = (unsigned char*)xb[r].raw;
+        } else {
+          void* p = nullptr;
+          CU(cudaIpcOpenMemHandle(&p, xb[r].h, cudaIpcMemLazyEnablePeerAccess));
+          m->xopened[r] = p; m->xpeer[r] = (unsigned char*)p;
+        }
+      }
+      // nobody may signal into a buffer that its owner is still clearing
+      NC(ncclAllReduce(m->d_flag, m->d_flag, 1, ncclInt, ncclSum, m->comm_sync, m->es));
+      CU(cudaStreamSynchronize(m->es));
+    }
     return TSDF_OK;
   };
   MX(body());
@@ -262,13 +338,17 @@ int tsdf_mgpu_integrate(tsdf_mgpu_handle m, int root, int on_device, const void*
 
 static int ensure_images(tsdf_mgpu* m, int w, int h) {
   const size_t need = (size_t)rows_per_rank(m, h) * m->world * w;
-  if (need > m->img_cap_px) {
-    CU(cudaStreamSynchronize(m->es));
-    for (unsigned char*& p : m->img) { cudaFree(p); p = nullptr; }
-    m->img_cap_px = 0;
-    for (unsigned char*& p : m->img) CU(cudaMalloc(&p, 4 * need));
-    m->img_cap_px = need;
-  }
+  if ((size_t)w * h > m->max_px || need > m->max_px + kRowSlack)
+    return fail(TSDF_E_INVALID, "view %dx%d exceeds max_image_pixels=%zu of this volume", w, h, m->max_px);
+  return TSDF_OK;
+}
+
+static int peer_barrier(tsdf_mgpu* m) {
+  PeerFlags pf{};
+  for (int r = 0; r < m->world; ++r) pf.flags[r] = reinterpret_cast<int*>(m->xpeer[r] + 3 * m->img_stride);
+  m->epoch++;
+  peer_barrier_kernel<<<1, 32, 0, m->es>>>(pf, m->rank, m->world, m->epoch, 4000000000ll, m->d_err);  // ~2 s
+  CU(cudaGetLastError());
   return TSDF_OK;
 }
 
@@ -280,20 +360,34 @@ int tsdf_mgpu_raycast(tsdf_mgpu_handle m, float max_depth, int w, int h, const f
   int rc = ensure_images(m, w, h);
   if (rc) return rc;
   const int rows = rows_per_rank(m, h), row0 = m->rank * rows;
-  if (m->world > 1) {  // every shard's Integrate has finished before any rank reads its voxels
-    Timed tm(m, T_BARRIER, m->es);
-    NC(ncclAllReduce(m->d_flag, m->d_flag, 1, ncclInt, ncclSum, m->comm_sync, m->es));
-  }
-  {
-    Timed tm(m, T_RAYCAST, m->es);
-    if (row0 < h) TS(tsdf_raycast_shared(m->eng, max_depth, w, h, K, q, t, row0, rows, m->img[0], m->img[1], m->img[2]));
-  }
-  if (m->world > 1) {  // in place: this rank's rows already sit at chunk `rank` of each image
-    Timed tm(m, T_ALLGATHER, m->es);
-    const size_t chunk = (size_t)rows * w * 4;
-    NC(ncclGroupStart());
-    for (int i = 0; i < 3; ++i) NC(ncclAllGather(m->img[i] + (size_t)m->rank * chunk, m->img[i], chunk, ncclChar, m->comm_sync, m->es));
-    NC(ncclGroupEnd());
+  if (m->world > 1 && m->fused) {
+    // fused exchange: no collective library on the engine stream.  Barrier (every shard's Integrate has finished before
+    // any rank reads its voxels) -> march with the finished rays stored into every rank's images -> barrier (all rows
+    // have arrived everywhere, and every peer is done reading this rank's voxels before its next Integrate)
+    { Timed tm(m, T_BARRIER, m->es); int rc2 = peer_barrier(m); if (rc2) return rc2; }
+    {
+      Timed tm(m, T_RAYCAST, m->es);
+      void* o[3][kMaxRanks];
+      for (int i = 0; i < 3; ++i) for (int r = 0; r < m->world; ++r) o[i][r] = m->xpeer[r] + (size_t)i * m->img_stride;
+      if (row0 < h) TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, row0, rows, m->world, o[0], o[1], o[2]));
+    }
+    { Timed tm(m, T_ALLGATHER, m->es); int rc2 = peer_barrier(m); if (rc2) return rc2; }
+  } else {
+    if (m->world > 1) {  // every shard's Integrate has finished before any rank reads its voxels
+      Timed tm(m, T_BARRIER, m->es);
+      NC(ncclAllReduce(m->d_flag, m->d_flag, 1, ncclInt, ncclSum, m->comm_sync, m->es));
+    }
+    {
+      Timed tm(m, T_RAYCAST, m->es);
+      if (row0 < h) TS(tsdf_raycast_shared(m->eng, max_depth, w, h, K, q, t, row0, rows, m->img[0], m->img[1], m->img[2]));
+    }
+    if (m->world > 1) {  // in place: this rank's rows already sit at chunk `rank` of each image
+      Timed tm(m, T_ALLGATHER, m->es);
+      const size_t chunk = (size_t)rows * w * 4;
+      NC(ncclGroupStart());
+      for (int i = 0; i < 3; ++i) NC(ncclAllGather(m->img[i] + (size_t)m->rank * chunk, m->img[i], chunk, ncclChar, m->comm_sync, m->es));
+      NC(ncclGroupEnd());
+    }
   }
   m->last_w = w; m->last_h = h;
   if (d_rgba) *d_rgba = m->img[0];
@@ -440,6 +534,9 @@ int tsdf_mgpu_synchronize(tsdf_mgpu_handle m) {
   CU(cudaStreamSynchronize(m->cs));
   const int rc = tsdf_synchronize(m->eng);
   CU(cudaStreamSynchronize(m->es));
+  int berr = 0;
+  CU(cudaMemcpy(&berr, m->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (berr) return fail(TSDF_E_CUDA, "peer barrier %d timed out: a rank of the volume stopped making progress", berr);
   if (rc != TSDF_OK) return fail(rc, "%s", tsdf_last_error());
   return TSDF_OK;
 }

@@ -19,7 +19,7 @@ void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& 
                            cudaStream_t st);
 void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
                            const SkipMap& M, int row0, int rows, uchar4* rgba, uchar4* normal, float* hit_depth,
-                           cudaStream_t st);
+                           int n_out, void* const* out_rgba, void* const* out_normal, void* const* out_depth, cudaStream_t st);
 void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, const SkipMap& M, uchar4* rgba,
                     uchar4* normal, float* hit_depth, unsigned long long* packed_keys, cudaStream_t st);
 

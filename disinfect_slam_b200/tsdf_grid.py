@@ -94,6 +94,9 @@ class TSDFGrid:
         check(self.L.tsdf_create(voxel_size, truncation, C.byref(cfg), C.byref(self.h)))
 
     def close(self):
+        if getattr(self, "_pin", None) is not None:
+            self._pin.free()
+            self._pin = None
         if getattr(self, "h", None):
             self.L.tsdf_destroy(self.h)
             self.h = None
@@ -193,14 +196,30 @@ class TSDFGrid:
                                          int(row0), int(rows), d_rgba, d_normal, d_depth))
 
     # ---- TSDFGrid::GatherValid / GatherVoxels (utils/tsdf/voxel_tsdf.cu:399-454) -------------------
-    def _gather(self, bbox):
+    def _gather(self, bbox, pinned=False, out=None):
+        """`out`: optional caller-owned (n, 4) float32 destination (e.g. a PinnedArray view sized for the largest query);
+        the records land in out[:n], which is returned."""
         n = C.c_int64(0)
         if bbox is None:
             check(self.L.tsdf_gather_valid(self.h, None, 0, C.byref(n)))
         else:
             bb = _f32(bbox, 6)
             check(self.L.tsdf_gather_in_bound(self.h, _p(bb), None, 0, C.byref(n)))
-        out = np.empty((n.value, 4), np.float32)
+        if out is not None:
+            if out.dtype != np.float32 or out.ndim != 2 or out.shape[1] != 4 or not out.flags["C_CONTIGUOUS"] or out.shape[0] < n.value:
+                raise ValueError(f"gather destination must be C-contiguous float32 (>= {n.value}, 4)")
+            out = out[:n.value]
+        elif pinned:
+            # grow-only pinned result buffer owned by this object: the DMA engine writes it directly (PCIe speed); the
+            # returned view is valid until the next pinned gather
+            if getattr(self, "_pin", None) is None or self._pin.array.shape[0] < n.value:
+                old = 0 if getattr(self, "_pin", None) is None else self._pin.array.shape[0]
+                if old:
+                    self._pin.free()
+                self._pin = PinnedArray((max(n.value, int(1.5 * old), 1 << 16), 4), np.float32)  # geometric growth: pinning memory is slow
+            out = self._pin.array[:n.value]
+        else:
+            out = np.empty((n.value, 4), np.float32)  # pageable: the engine pipelines the copy through pinned staging
         if n.value:
             check(self.L.tsdf_gather_fetch(self.h, _p(out), n.value))
         return out
@@ -231,11 +250,11 @@ class TSDFGrid:
             check(self.L.tsdf_gather_in_bound(self.h, _p(bb), None, 0, C.byref(n)))
         return int(n.value)
 
-    def GatherValid(self):
-        return self._gather(None)
+    def GatherValid(self, pinned=False, out=None):
+        return self._gather(None, pinned, out)
 
-    def GatherVoxels(self, volumn):
-        return self._gather(tuple(volumn))
+    def GatherVoxels(self, volumn, pinned=False, out=None):
+        return self._gather(tuple(volumn), pinned, out)
 
     # ---- bookkeeping / parity access ---------------------------------------------------------------
     def NumActiveBlock(self):  # VoxelHashTable::NumActiveBlock, voxel_hash.cu:200

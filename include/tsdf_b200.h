@@ -155,6 +155,13 @@ int tsdf_ipc_attach(tsdf_handle h, int shard_count, const void* blobs /* shard_c
 int tsdf_peer_attach_local(tsdf_handle h, int shard_count, const tsdf_handle* shards);
 int tsdf_raycast_shared(tsdf_handle h, float max_depth, int width, int height, const float K[4], const float q_xyzw[4],
                         const float t_xyz[3], int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth);
+/* Same march, with the exchange of the results fused into the kernel: every finished ray is stored into the HxW images
+ * of n_dest destinations (device pointers, typically the image buffers of every rank mapped as peer memory; entries or
+ * whole arrays may be NULL) -- posted stores over NVLink while the march runs, instead of a local image plus an
+ * all-gather afterwards.  The caller orders the destinations' readers with its own barrier. */
+int tsdf_raycast_shared_scatter(tsdf_handle h, float max_depth, int width, int height, const float K[4],
+                                const float q_xyzw[4], const float t_xyz[3], int row0, int rows, int n_dest,
+                                void* const* d_rgba, void* const* d_normal, void* const* d_hit_depth);
 
 /* TSDFGrid::GatherValid()                               utils/tsdf/voxel_tsdf.cu:399-425
  * TSDFGrid::GatherVoxels(BoundingCube<float>)           utils/tsdf/voxel_tsdf.cu:427-454

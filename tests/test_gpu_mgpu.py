@@ -124,15 +124,19 @@ def test_data_plane_with_one_shard_matches_oracle(tsdf_lib):
     check_against_oracle(res, 1, cfg, N_FRAMES)
 
 
-def _proc(rank, world, nccl_id, q):
+def _proc(rank, world, nccl_id, q, exchange):
     try:
+        os.environ["TSDF_MGPU_EXCHANGE"] = exchange  # read by tsdf_mgpu_create
         q.put((rank, run_rank(rank, world, nccl_id, CFG, N_FRAMES)))
     except Exception:
         import traceback
         q.put((rank, {"error": traceback.format_exc()}))
 
 
-def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib):
+@pytest.mark.parametrize("exchange", ["fused", "nccl"])
+def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib, exchange):
+    """exchange = fused: peer-barrier kernels + image rows stored into every rank's buffers by the march kernel (the
+    product path); nccl: ncclAllReduce barrier + in-place ncclAllGather (kept for comparison)."""
     if n_gpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2); the bench's sharded leg carries the driver-visible parity check")
     import multiprocessing as mp
@@ -141,7 +145,7 @@ def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib):
     nccl_id = mgpu.unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_proc, args=(r, world, nccl_id, q)) for r in range(world)]
+    procs = [ctx.Process(target=_proc, args=(r, world, nccl_id, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}

@@ -120,6 +120,12 @@ def test_baseline_config1_100_frames_integrate_and_gather_valid(tg):
     assert rep["n_blocks_engine"] > 10000
     rep = compare.compare_gather(g.GatherValid(), o.gather(), "config1 GatherValid after 100 frames")
     assert rep["tsdf_bit_exact"] and rep["n_voxels"] == 512 * g.NumActiveBlock()
+    # 128 MB of records: the pageable path (16 MB chunks through pinned staging, 4 host threads) and the pinned path
+    # (one DMA into caller memory) deliver the same bytes
+    a, b = g.GatherValid(), g.GatherValid(pinned=True)
+    assert a.nbytes > 100e6 and np.array_equal(compare.canonical_gather(a).view(np.uint32), compare.canonical_gather(b).view(np.uint32))
+    tris = g.ExtractMesh()  # the mesh result takes the same host path
+    assert tris.nbytes > 32e6 and np.isfinite(tris).all()
     cam = tg.CameraParams(f["K"], cfg.height, cfg.width)
     compare.compare_raycast(g.RayCast(cfg.max_depth, cam, (f["q"], f["t"])),
                             o.raycast(cfg.max_depth, cfg.width, cfg.height, f["K"], f["q"], f["t"])[:3], "config1 view after 100 frames")
