@@ -518,12 +518,62 @@ def main():
     del engs
 
     # ---------------- leg 3: end to end through the host-buffer C ABI ----------------
-    # Every step uploads each stream's frame from pinned host memory (15 B/px) and brings both rendered images and the
-    # hit depth back to pinned host memory (12 B/px), one host thread per stream (what a TSDFSystem worker is).
-    #   pipelined: tsdf_integrate_async + tsdf_raycast_async -- the copies of frame k overlap the kernels of its
-    #              neighbours; a frame's images are waited for (tsdf_raycast_wait) one frame later, all of them inside
-    #              the timed region (the `e2e` key)
-    #   sync:      tsdf_integrate + tsdf_raycast, the reference's blocking call pattern (`e2e_sync`)
+    # Every step uploads each stream's frame from pinned host memory and brings the rendered rgba + normal images -- what
+    # TSDFGrid::RayCast delivers -- back to pinned host memory, all inside the timed region.
+    #   e2e       tsdf_streams_run: ONE host thread per GPU drives all streams (tsdf_integrate_enqueue +
+    #             tsdf_raycast_async + tsdf_raycast_wait one step later); float32 planes, 15 B/px in, 8 B/px out
+    #   e2e_u16   the same loop on the sensor's own formats (tsdf_integrate_u16: 16-bit depth + probabilities, 9 B/px in)
+    #   e2e_sync  tsdf_integrate + tsdf_raycast (+ hit depth), blocking, one Python thread per stream: the reference's
+    #             call pattern
+    def run_e2e_native(fmt16):
+        engs = make_engines(blocking=False)
+        # every frame = one pinned block [rgb | depth | ht | lt] (what a capture thread fills); the 16-bit planes are
+        # what a sensor / log delivers (quantised once, outside the timed region)
+        keep, per_stream = [], []
+        q16 = lambda x, sc: np.clip(np.rint(x.astype(np.float64) * sc), 0, 65535).astype(np.uint16)  # noqa: E731
+        for st in streams:
+            fl = []
+            for i in range(n_frames):
+                if fmt16:
+                    blk, d = tsdf_grid.packed_pinned_frame(st["rgb"][i], q16(st["depth"][i], cfg.depth_factor), q16(st["ht"][i], 65535), q16(st["lt"][i], 65535))
+                else:
+                    blk, d = tsdf_grid.packed_pinned_frame(st["rgb"][i], st["depth"][i], st["ht"][i], st["lt"][i])
+                keep.append(blk)
+                fl.append(dict(d, q=st["q"][i], t=st["t"][i]))
+            per_stream.append(fl)
+        frames = tsdf_grid.make_host_frames(per_stream)
+        oblk, rgba, normal, _ = tsdf_grid.packed_pinned_images(H, Wd, 2 * B)
+
+        def run(first, count):
+            tsdf_grid.run_streams(engs, frames, first, count, Wd, H, cfg.max_depth, streams[0]["K"], depthmap_factor=cfg.depth_factor, raycast=True,
+                                  rgba=rgba, normal=normal, hit_depth=None)
+
+        run(0, W)
+        barrier()
+        t_a = time.perf_counter()
+        run(W, K)  # returns after every engine has been synchronised: the last images are in host memory
+        t_b = time.perf_counter()
+        windows.append((t_a, t_b))
+        e2e_s = t_b - t_a
+        if world > 1:
+            tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
+        checksum = float(sum(int(rgba[2 * b + ((W + K - 1) & 1)][::97, ::89].sum()) for b in range(B)))
+        bpp_in = 9 if fmt16 else 15
+        res = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bpp_in * npx * B, "d2h_bytes_per_step": 8 * npx * B + 128 * B,
+               "api": ("tsdf_streams_run: two host threads per GPU drive its %d streams -- %s (no host wait), tsdf_raycast_async, tsdf_raycast_wait one "
+                       "step later; every frame is one pinned block [rgb | depth | ht | lt] (one DMA transfer), rgba + normal of every frame reach one "
+                       "pinned block of host memory inside the timed region"
+                       % (B, "tsdf_integrate_u16(TSDF_FRAME_NOWAIT): uint16 depth / ht / lt converted on the GPU" if fmt16 else "tsdf_integrate_enqueue: float32 planes")),
+               "ms_per_step": 1e3 * e2e_s / K, "last_frame_rgba_checksum": checksum, "host_cores": os.cpu_count(), "host_threads_all_ranks": 2 * world,
+               "h2d_gbs_per_gpu": B * K * bpp_in * npx / e2e_s / 1e9, "d2h_gbs_per_gpu": B * K * 8 * npx / e2e_s / 1e9}
+        for g in engs:
+            g.close()
+        for p_ in oblk + keep:
+            p_.free()
+        return res
+
     def run_e2e(pipelined):
         engs = make_engines(blocking=oversubscribed)
         houts = [[(tsdf_grid.PinnedArray((H, Wd, 4), np.uint8), tsdf_grid.PinnedArray((H, Wd, 4), np.uint8),
@@ -578,7 +628,7 @@ def main():
         res = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * npx * B, "d2h_bytes_per_step": 12 * npx * B + 64 * B,
                "api": ("tsdf_integrate_async + tsdf_raycast_async + tsdf_raycast_wait (pipelined, pinned host buffers; every frame's rgba + normal + "
                        "hit depth reach host memory inside the timed region, waited for one frame later)" if pipelined else
-                       "tsdf_integrate + tsdf_raycast (synchronous, pinned host buffers)") + ", one host thread per stream"
+                       "tsdf_integrate + tsdf_raycast (synchronous, pinned host buffers; rgba + normal + hit depth)") + ", one Python host thread per stream"
                       + (", TSDF_FLAG_BLOCKING_SYNC (waiting threads yield: they would occupy half of the host cores or more)" if oversubscribed else ""),
                "ms_per_step": 1e3 * e2e_s / K, "last_frame_rgba_checksum": checksum, "host_cores": os.cpu_count(),
                "engine_threads_all_ranks": world * B}
@@ -590,12 +640,13 @@ def main():
                     a.free()
         return res
 
-    e2e = e2e_sync = None
+    e2e = e2e_sync = e2e_u16 = None
     if not args.no_e2e:
         e2e_sync = run_e2e(False)
-        e2e = run_e2e(True)
+        e2e_u16 = run_e2e_native(True)
+        e2e = run_e2e_native(False)
         # what the e2e number runs against: the host <-> device copy bandwidth of this box, pinned memory, both directions
-        # busy at once (256 MB each, best of 5) -- the e2e leg moves 15 B/px in and 12 B/px out per frame
+        # busy at once (256 MB each, best of 5) -- the e2e leg moves 15 B/px in and 8 B/px out per frame
         try:
             nb = 256 << 20
             hp_in, hp_out = torch.empty(nb, dtype=torch.uint8, pin_memory=True), torch.empty(nb, dtype=torch.uint8, pin_memory=True)
@@ -617,7 +668,7 @@ def main():
                     best[mode] = max(best[mode], nb / dt / 1e9)
             e2e["pcie_measured_gbs"] = {"h2d_alone": best["h2d"], "d2h_alone": best["d2h"], "each_direction_when_both_run": best["both"]}
             e2e["h2d_gbs_in_e2e"] = e2e["value"] / world * 15 * npx / 1e9
-            e2e["d2h_gbs_in_e2e"] = e2e["value"] / world * 12 * npx / 1e9
+            e2e["d2h_gbs_in_e2e"] = e2e["value"] / world * 8 * npx / 1e9
             del hp_in, hp_out, d_in, d_out
         except Exception as ex:  # supplementary only
             e2e["pcie_measured_gbs"] = {"error": repr(ex)}
@@ -697,6 +748,7 @@ def main():
                     "mrays_per_s_kernel_only": npx * ph_n.get("raycast", 0) / (ph_ms.get("raycast", 1e-9) * 1e-3) / 1e6,
                     "note": "skip-map build + march; issue/latency bound (ncu: DRAM < 6 % of peak), not an HBM-roofline kernel"},
         "e2e": e2e,
+        "e2e_u16": e2e_u16,
         "e2e_sync": e2e_sync,
         # per frame: frame_allocate, select_visible, integrate_carve + skip_fill, skip_mark, 3 x skip_pass, raycast
         "gpu_launches": 9 * B * K,

@@ -25,6 +25,12 @@ class Config(C.Structure):
                 ("shard_count", C.c_int32), ("flags", C.c_int32)]
 
 
+class HostFrame(C.Structure):
+    """tsdf_host_frame (include/tsdf_b200.h)."""
+    _fields_ = [("rgb", C.c_void_p), ("depth", C.c_void_p), ("ht", C.c_void_p), ("lt", C.c_void_p),
+                ("q", C.c_float * 4), ("t", C.c_float * 3), ("format", C.c_int32)]
+
+
 class Counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_active_pre", "n_new", "n_visible", "n_updated", "n_carved",
                                          "n_active_post", "n_candidates", "reserved")]
@@ -42,6 +48,9 @@ SYMBOLS = {
     "tsdf_integrate": (_i32, _FRAME),
     "tsdf_integrate_async": (_i32, _FRAME),
     "tsdf_integrate_device": (_i32, _FRAME + [_vp]),
+    "tsdf_integrate_enqueue": (_i32, _FRAME),
+    "tsdf_streams_run": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _i32, _vp, _vp, _vp]),
+    "tsdf_integrate_u16": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _i32]),
     "tsdf_raycast": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsdf_raycast_async": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsdf_raycast_wait": (_i32, [_vp]),

@@ -39,9 +39,11 @@ enum { PH_UPLOAD = 0, PH_ALLOC, PH_SELECT, PH_INTEGRATE, PH_RAYCAST, PH_GATHER, 
 
 struct FrameBuf {
   unsigned char* rgb = nullptr; float *depth = nullptr, *ht = nullptr, *lt = nullptr;
+  unsigned char* packed = nullptr;
   Texel* tex = nullptr;
   cudaEvent_t uploaded = nullptr, done = nullptr;
-  int* h_ctr = nullptr;  // pinned copy of the device counters after this frame
+  int* h_ctr = nullptr;  // pinned (mapped) copy of the device counters after this frame
+  int* d_h_ctr = nullptr;  // the same memory as the device addresses it
   bool in_flight = false;
 };
 }  // namespace
@@ -66,10 +68,11 @@ struct tsdf_engine {
   uint64_t volume_epoch = 1, skip_epoch = 0;  // host side: a mutating call was enqueued since the map was last looked at
   int skip_gen = 0;    // number of skip-map build attempts (see skip_fill_kernel)
   int serial = 0;      // number of mutating calls (frames, allocate / delete lists); DeviceState::serial of the current one
-  uchar4 *rgba = nullptr, *normal = nullptr; float* hit_depth = nullptr;
   // pipelined RayCast (tsdf_raycast_async): two sets of output images (set 0 = the three above, set 1 allocated on first
   // use), rendered on `stream`, copied to the host on `d2h_stream` while the next frame's kernels run
-  struct RcSet { uchar4 *rgba = nullptr, *normal = nullptr; float* depth = nullptr; cudaEvent_t rendered = nullptr, copied = nullptr; bool pending = false; } rc[2];
+  // each set is ONE block [rgba | normal | hit depth] laid out for the current image size, so that host images that are
+  // adjacent in memory are downloaded with one transfer
+  struct RcSet { unsigned char* block = nullptr; cudaEvent_t rendered = nullptr, copied = nullptr; bool pending = false; } rc[2];
   int rc_cur = 0;
   cudaStream_t d2h_stream = nullptr;
   float4* gather_out = nullptr; size_t gather_cap = 0; int64_t gather_n = 0;
@@ -169,12 +172,10 @@ static void next_serial(tsdf_engine* e) {
 }
 
 // kernels of one frame, enqueued on the compute stream; no host synchronisation
-static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned char* rgb, const float* depth,
-                          const float* ht, const float* lt, FrameBuf& f) {
-  next_serial(e);
-  cudaMemsetAsync(e->S.ctr + C_PER_CALL, 0, sizeof(int) * (C_COUNT - C_PER_CALL), e->stream);
+static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const FrameInput& in, FrameBuf& f) {
+  next_serial(e);  // (the per-call counters are zero here: cleared by the previous frame's publish kernel / after_mutation)
   phase_begin(e, PH_ALLOC, e->stream);
-  launch_frame_allocate(e->S, P, rgb, depth, ht, lt, f.tex, e->stream);
+  launch_frame_allocate(e->S, P, in, f.tex, e->stream);
   phase_end(e, PH_ALLOC, e->stream);
   phase_begin(e, PH_SELECT, e->stream);
   launch_select_visible(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, e->num_sms, e->stream);
@@ -182,10 +183,15 @@ static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const unsigned c
   phase_begin(e, PH_INTEGRATE, e->stream);
   launch_integrate_carve(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, f.tex, e->num_sms, e->stream);
   phase_end(e, PH_INTEGRATE, e->stream);
-  cudaMemcpyAsync(f.h_ctr, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream);
+  launch_publish_counters(e->S, f.d_h_ctr, e->stream);  // a store into mapped host memory: no copy engine on the compute stream
   cudaEventRecord(f.done, e->stream);
   f.in_flight = true;
   e->volume_epoch++;
+}
+static FrameInput f32_input(const void* rgb, const void* depth, const void* ht, const void* lt) {
+  FrameInput in{};
+  in.rgb = (const unsigned char*)rgb; in.depth = depth; in.ht = ht; in.lt = lt;
+  return in;
 }
 
 // wait for the frame that used slot `s`, fold its counters into the host mirror, surface errors
@@ -313,15 +319,17 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   const size_t npx = (size_t)cfg.max_image_pixels;
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
+    CUX(cudaMalloc(&f.packed, 15 * npx + 64));  // a frame whose planes are packed back to back in host memory arrives here with ONE copy
     CUX(cudaMalloc(&f.rgb, 3 * npx)); CUX(cudaMalloc(&f.depth, 4 * npx)); CUX(cudaMalloc(&f.ht, 4 * npx)); CUX(cudaMalloc(&f.lt, 4 * npx));
     CUX(cudaMalloc(&f.tex, sizeof(Texel) * npx));
     const unsigned evf = cudaEventDisableTiming | (e->blocking_sync ? cudaEventBlockingSync : 0u);
     CUX(cudaEventCreateWithFlags(&f.uploaded, evf));
     CUX(cudaEventCreateWithFlags(&f.done, evf));
-    CUX(cudaMallocHost(&f.h_ctr, sizeof(int) * C_COUNT));
+    CUX(cudaHostAlloc(&f.h_ctr, sizeof(int) * C_COUNT, cudaHostAllocMapped));
     memset(f.h_ctr, 0, sizeof(int) * C_COUNT);
+    CUX(cudaHostGetDevicePointer(&f.d_h_ctr, f.h_ctr, 0));
   }
-  CUX(cudaMalloc(&e->rgba, sizeof(uchar4) * npx)); CUX(cudaMalloc(&e->normal, sizeof(uchar4) * npx)); CUX(cudaMalloc(&e->hit_depth, sizeof(float) * npx));
+  CUX(cudaMalloc(&e->rc[0].block, 12 * npx));
   CUX(cudaMallocHost(&e->h_scalar, sizeof(int) * C_COUNT));
   launch_init_state(S, e->stream);
   CUX(cudaGetLastError());
@@ -337,7 +345,7 @@ int tsdf_destroy(tsdf_handle e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
-  cudaFree(e->rc[1].rgba); cudaFree(e->rc[1].normal); cudaFree(e->rc[1].depth);
+  cudaFree(e->rc[0].block); cudaFree(e->rc[1].block);
   for (int i = 0; i < 2; ++i) { if (e->rc[i].rendered) cudaEventDestroy(e->rc[i].rendered); if (e->rc[i].copied) cudaEventDestroy(e->rc[i].copied); }
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
   cudaFree(e->visible); cudaFree(e->selected); cudaFree(e->mesh_out); cudaFree(e->mesh_counter);
@@ -346,12 +354,12 @@ int tsdf_destroy(tsdf_handle e) {
   cudaFree(e->d_self); cudaFree(e->d_peers);
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
-    cudaFree(f.rgb); cudaFree(f.depth); cudaFree(f.ht); cudaFree(f.lt); cudaFree(f.tex);
+    cudaFree(f.packed); cudaFree(f.rgb); cudaFree(f.depth); cudaFree(f.ht); cudaFree(f.lt); cudaFree(f.tex);
     if (f.uploaded) cudaEventDestroy(f.uploaded);
     if (f.done) cudaEventDestroy(f.done);
     if (f.h_ctr) cudaFreeHost(f.h_ctr);
   }
-  cudaFree(e->rgba); cudaFree(e->normal); cudaFree(e->hit_depth); cudaFree(e->gather_out);
+  cudaFree(e->gather_out);
   if (e->h_scalar) cudaFreeHost(e->h_scalar);
   for (int i = 0; i < 2; ++i) { if (e->bounce[i]) cudaFreeHost(e->bounce[i]); if (e->bounce_ev[i]) cudaEventDestroy(e->bounce_ev[i]); }
   if (e->ev_block) cudaEventDestroy(e->ev_block);
@@ -363,10 +371,17 @@ int tsdf_destroy(tsdf_handle e) {
   return TSDF_OK;
 }
 
-int tsdf_integrate_async(tsdf_handle e, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int w,
-                         int h, float max_depth, const float K[4], const float q[4], const float t[3]) {
-  int rc = check_frame_args(e, rgb, depth, ht, lt, w, h, K, q, t);
-  if (rc) return rc;
+// Host frame -> staging set -> kernels.  Planes: rgb u8x3 always; depth / ht / lt float32 (bytes_px = 4) or uint16
+// (bytes_px = 2, converted inside the allocation kernel); ht == lt == nullptr: no probability planes are uploaded at all.
+// wait_upload: block until the DMA engine has read the host buffers (they may then be reused: what tsdf_integrate_async
+// promises); without it the call returns at once and the buffers must stay untouched until the frame has retired.
+static int submit_host_frame(tsdf_engine* e, const uint8_t* rgb, const void* depth, const void* ht, const void* lt, int depth_u16,
+                             int prob_u16, float depth_scale, float prob_scale, int w, int h, float max_depth, const float K[4],
+                             const float q[4], const float t[3], bool wait_upload) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  if (!rgb || !depth || !K || !q || !t || ((ht == nullptr) != (lt == nullptr))) return fail(TSDF_E_INVALID, "null image / camera pointer");
+  if (w <= 0 || h <= 0 || (int64_t)w * h > e->cfg.max_image_pixels)
+    return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
   CU(cudaSetDevice(e->device));
   const int s = e->cur;
   FrameBuf& f = e->fb[s];
@@ -377,21 +392,63 @@ int tsdf_integrate_async(tsdf_handle e, const uint8_t* rgb, const float* depth, 
   const size_t n = (size_t)w * h;
   // uploads on the copy stream (they overlap the previous frame's kernels on the compute stream)
   phase_begin(e, PH_UPLOAD, e->copy_stream);
-  CU(cudaMemcpyAsync(f.rgb, rgb, 3 * n, cudaMemcpyHostToDevice, e->copy_stream));
-  CU(cudaMemcpyAsync(f.depth, depth, 4 * n, cudaMemcpyHostToDevice, e->copy_stream));
-  CU(cudaMemcpyAsync(f.ht, ht, 4 * n, cudaMemcpyHostToDevice, e->copy_stream));
-  CU(cudaMemcpyAsync(f.lt, lt, 4 * n, cudaMemcpyHostToDevice, e->copy_stream));
+  const size_t b_rgb = 3 * n, b_d = (depth_u16 ? 2 : 4) * n, b_p = (prob_u16 ? 2 : 4) * n;
+  const unsigned char *d_rgb = f.rgb, *d_depth = (const unsigned char*)f.depth, *d_ht = (const unsigned char*)f.ht, *d_lt = (const unsigned char*)f.lt;
+  // Planes packed back to back in host memory ([rgb | depth | ht | lt], e.g. one pinned block per frame filled by the
+  // capture threads) travel as ONE DMA transfer: with uploads and image downloads sharing the link, a few large
+  // transfers reach ~48 GB/s per direction on this platform where four 2 MB ones reach ~34 (profiles/).
+  const bool packed = (b_rgb % 4 == 0) && (const unsigned char*)depth == rgb + b_rgb &&
+                      (!ht || ((const unsigned char*)ht == (const unsigned char*)depth + b_d && (const unsigned char*)lt == (const unsigned char*)ht + b_p));
+  bool packed_done = false;
+  if (packed) {  // (adjacent planes of separate pinned allocations cannot travel in one transfer: the runtime refuses, see below)
+    packed_done = cudaMemcpyAsync(f.packed, rgb, b_rgb + b_d + (ht ? 2 * b_p : 0), cudaMemcpyHostToDevice, e->copy_stream) == cudaSuccess;
+    if (!packed_done) cudaGetLastError();
+  }
+  if (packed_done) {
+    d_rgb = f.packed; d_depth = f.packed + b_rgb; d_ht = d_depth + b_d; d_lt = d_ht + b_p;
+  } else {
+    CU(cudaMemcpyAsync(f.rgb, rgb, b_rgb, cudaMemcpyHostToDevice, e->copy_stream));
+    CU(cudaMemcpyAsync(f.depth, depth, b_d, cudaMemcpyHostToDevice, e->copy_stream));
+    if (ht) {
+      CU(cudaMemcpyAsync(f.ht, ht, b_p, cudaMemcpyHostToDevice, e->copy_stream));
+      CU(cudaMemcpyAsync(f.lt, lt, b_p, cudaMemcpyHostToDevice, e->copy_stream));
+    }
+  }
   phase_end(e, PH_UPLOAD, e->copy_stream);
   CU(cudaEventRecord(f.uploaded, e->copy_stream));
   CU(cudaStreamWaitEvent(e->stream, f.uploaded, 0));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
-  enqueue_frame(e, P, f.rgb, f.depth, f.ht, f.lt, f);
+  FrameInput in = f32_input(d_rgb, d_depth, ht ? d_ht : nullptr, ht ? d_lt : nullptr);
+  in.depth_u16 = depth_u16; in.prob_u16 = prob_u16; in.depth_scale = depth_scale; in.prob_scale = prob_scale;
+  enqueue_frame(e, P, in, f);
   CU(cudaGetLastError());
   e->last_slot = s;
   e->cur = 1 - s;
-  // the host buffers are reusable once the copies have been issued from them
-  CU(cudaEventSynchronize(f.uploaded));
+  if (wait_upload) CU(cudaEventSynchronize(f.uploaded));  // the host buffers are reusable once the copies have been issued from them
   return rc_old;
+}
+
+int tsdf_integrate_async(tsdf_handle e, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int w,
+                         int h, float max_depth, const float K[4], const float q[4], const float t[3]) {
+  if (!ht || !lt) return fail(TSDF_E_INVALID, "null image / camera pointer");
+  return submit_host_frame(e, rgb, depth, ht, lt, 0, 0, 0.f, 0.f, w, h, max_depth, K, q, t, true);
+}
+
+int tsdf_integrate_enqueue(tsdf_handle e, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int w,
+                           int h, float max_depth, const float K[4], const float q[4], const float t[3]) {
+  return submit_host_frame(e, rgb, depth, ht, lt, 0, 0, 0.f, 0.f, w, h, max_depth, K, q, t, false);
+}
+
+int tsdf_integrate_u16(tsdf_handle e, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht, const uint16_t* lt, int w,
+                       int h, float depthmap_factor, float max_depth, const float K[4], const float q[4], const float t[3], int flags) {
+  if (!(depthmap_factor > 0.f)) return fail(TSDF_E_INVALID, "depthmap_factor must be > 0");
+  // img.convertTo(CV_32FC1, 1. / depth_scale) and (..., 1. / 65535): the double factor is cast to float inside OpenCV
+  const float ds = (float)(1. / (double)depthmap_factor), ps = (float)(1. / 65535);
+  const int rc = submit_host_frame(e, rgb, depth, ht, lt, 1, 1, ds, ps, w, h, max_depth, K, q, t, (flags & TSDF_FRAME_NOWAIT) == 0);
+  if (flags & (TSDF_FRAME_ASYNC | TSDF_FRAME_NOWAIT)) return rc;
+  if (rc == TSDF_E_INVALID || rc == TSDF_E_CUDA || rc == TSDF_E_NO_DEVICE) return rc;
+  const int rc2 = drain(e);
+  return rc2 ? rc2 : rc;
 }
 
 int tsdf_integrate(tsdf_handle e, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int w, int h,
@@ -414,11 +471,77 @@ int tsdf_integrate_device(tsdf_handle e, const void* d_rgb, const void* d_depth,
   if (rc_old == TSDF_E_CUDA) return rc_old;
   if (after_event) CU(cudaStreamWaitEvent(e->stream, (cudaEvent_t)after_event, 0));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
-  enqueue_frame(e, P, (const unsigned char*)d_rgb, (const float*)d_depth, (const float*)d_ht, (const float*)d_lt, f);
+  enqueue_frame(e, P, f32_input(d_rgb, d_depth, d_ht, d_lt), f);
   CU(cudaGetLastError());
   e->last_slot = s;
   e->cur = 1 - s;
   return rc_old;
+}
+
+// A few host threads, many independent engines (streams) on one GPU -- the loop a multi-camera server runs.  Per step and
+// stream: enqueue the frame (no wait: pinned buffers), enqueue the view and its copies to pinned host memory, then make
+// sure the PREVIOUS step's images of that stream have arrived (they were enqueued a whole step ago, so this rarely
+// blocks).  Nothing in the loop waits for the GPU to finish the step it has just enqueued.  One thread issues about
+// thirty CUDA calls per frame, i.e. it feeds ~4 k frames/s; the streams are therefore split over `threads` host threads
+// (default 2, TSDF_STREAMS_THREADS) -- still far fewer than one blocking thread per stream.
+static int streams_worker(int n_streams, const tsdf_handle* engines, const tsdf_host_frame* frames, int n_frames, int first, int count,
+                          int w, int h, float depthmap_factor, float max_depth, const float K[4], int raycast, uint8_t* const* rgba,
+                          uint8_t* const* normal, float* const* hit_depth, int b0, int b1, char* err, size_t err_len) {
+  int deferred = TSDF_OK;
+  auto bail = [&](int rc) { snprintf(err, err_len, "%s", tsdf_last_error()); return rc; };
+  for (int i = first; i < first + count; ++i) {
+    for (int b = b0; b < b1; ++b) {
+      const tsdf_host_frame& f = frames[(size_t)b * n_frames + (i % n_frames)];
+      int rc;
+      if (f.format == TSDF_FORMAT_U16)
+        rc = tsdf_integrate_u16(engines[b], (const uint8_t*)f.rgb, (const uint16_t*)f.depth, (const uint16_t*)f.ht, (const uint16_t*)f.lt, w, h,
+                                depthmap_factor, max_depth, K, f.q_xyzw, f.t_xyz, TSDF_FRAME_NOWAIT);
+      else
+        rc = tsdf_integrate_enqueue(engines[b], (const uint8_t*)f.rgb, (const float*)f.depth, (const float*)f.ht, (const float*)f.lt, w, h,
+                                    max_depth, K, f.q_xyzw, f.t_xyz);
+      if (rc == TSDF_E_POOL_EXHAUSTED || rc == TSDF_E_TABLE_FULL) { deferred = rc; rc = TSDF_OK; }
+      if (rc) return bail(rc);
+      if (raycast) {
+        const int o = 2 * b + (i & 1);  // two sets of host images per stream, used alternately
+        rc = tsdf_raycast_async(engines[b], max_depth, w, h, K, f.q_xyzw, f.t_xyz, rgba ? rgba[o] : nullptr, normal ? normal[o] : nullptr,
+                                hit_depth ? hit_depth[o] : nullptr);
+        if (rc) return bail(rc);
+        if (i > first) { rc = tsdf_raycast_wait(engines[b]); if (rc) return bail(rc); }
+      }
+    }
+  }
+  for (int b = b0; b < b1; ++b) {
+    const int rc = tsdf_synchronize(engines[b]);
+    if (rc == TSDF_E_POOL_EXHAUSTED || rc == TSDF_E_TABLE_FULL) deferred = rc;
+    else if (rc) return bail(rc);
+  }
+  if (deferred) snprintf(err, err_len, "%s", tsdf_last_error());
+  return deferred;
+}
+
+int tsdf_streams_run(int n_streams, const tsdf_handle* engines, const tsdf_host_frame* frames, int n_frames, int first, int count,
+                     int w, int h, float depthmap_factor, float max_depth, const float K[4], int raycast, uint8_t* const* rgba,
+                     uint8_t* const* normal, float* const* hit_depth) {
+  if (n_streams <= 0 || !engines || !frames || n_frames <= 0 || first < 0 || count < 0 || !K) return fail(TSDF_E_INVALID, "bad argument");
+  int n_threads = 2;
+  if (const char* v = getenv("TSDF_STREAMS_THREADS")) n_threads = atoi(v);
+  n_threads = std::max(1, std::min(n_threads, n_streams));
+  std::vector<int> rcs(n_threads, TSDF_OK);
+  std::vector<std::vector<char>> errs(n_threads, std::vector<char>(512, 0));
+  auto part = [&](int t) {
+    const int b0 = (int)((long long)n_streams * t / n_threads), b1 = (int)((long long)n_streams * (t + 1) / n_threads);
+    rcs[t] = streams_worker(n_streams, engines, frames, n_frames, first, count, w, h, depthmap_factor, max_depth, K, raycast, rgba, normal,
+                            hit_depth, b0, b1, errs[t].data(), errs[t].size());
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(part, t);
+  part(0);
+  for (auto& x : th) x.join();
+  for (int t = 0; t < n_threads; ++t)
+    if (rcs[t] != TSDF_OK && rcs[t] != TSDF_E_POOL_EXHAUSTED && rcs[t] != TSDF_E_TABLE_FULL) return fail(rcs[t], "%s", errs[t].data());
+  for (int t = 0; t < n_threads; ++t)
+    if (rcs[t] != TSDF_OK) return fail(rcs[t], "%s", errs[t].data());
+  return TSDF_OK;
 }
 
 int tsdf_synchronize(tsdf_handle e) {
@@ -448,6 +571,23 @@ int tsdf_raycast_device(tsdf_handle e, float max_depth, int w, int h, const floa
   return TSDF_OK;
 }
 
+// [rgba | normal | hit depth] of n pixels each -> host.  Host images that follow one another in memory go in one transfer.
+static cudaError_t download_images(tsdf_engine* e, const unsigned char* block, size_t n, uint8_t* rgba, uint8_t* normal, float* hit_depth,
+                                   cudaStream_t st) {
+  (void)e;
+  cudaError_t r = cudaSuccess;
+  if (rgba && normal == rgba + 4 * n && (!hit_depth || (uint8_t*)hit_depth == normal + 4 * n)) {
+    // adjacent addresses may still belong to separate pinned allocations, which one transfer cannot span: the runtime
+    // then refuses (nothing is enqueued) and the images go one by one
+    if (cudaMemcpyAsync(rgba, block, (hit_depth ? 12 : 8) * n, cudaMemcpyDeviceToHost, st) == cudaSuccess) return cudaSuccess;
+    cudaGetLastError();
+  }
+  if (rgba) r = cudaMemcpyAsync(rgba, block, 4 * n, cudaMemcpyDeviceToHost, st);
+  if (r == cudaSuccess && normal) r = cudaMemcpyAsync(normal, block + 4 * n, 4 * n, cudaMemcpyDeviceToHost, st);
+  if (r == cudaSuccess && hit_depth) r = cudaMemcpyAsync(hit_depth, block + 8 * n, 4 * n, cudaMemcpyDeviceToHost, st);
+  return r;
+}
+
 int tsdf_raycast_async(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
                        uint8_t* rgba, uint8_t* normal, float* hit_depth) {
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
@@ -456,21 +596,18 @@ int tsdf_raycast_async(tsdf_handle e, float max_depth, int w, int h, const float
   if (!e->d2h_stream) {  // first use: second image set, copy stream, events
     const size_t npx = (size_t)e->cfg.max_image_pixels;
     CU(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
-    e->rc[0].rgba = e->rgba; e->rc[0].normal = e->normal; e->rc[0].depth = e->hit_depth;
-    CU(cudaMalloc(&e->rc[1].rgba, sizeof(uchar4) * npx)); CU(cudaMalloc(&e->rc[1].normal, sizeof(uchar4) * npx)); CU(cudaMalloc(&e->rc[1].depth, sizeof(float) * npx));
+    CU(cudaMalloc(&e->rc[1].block, 12 * npx));
     const unsigned evf = cudaEventDisableTiming | (e->blocking_sync ? cudaEventBlockingSync : 0u);
     for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&e->rc[i].rendered, evf)); CU(cudaEventCreateWithFlags(&e->rc[i].copied, evf)); }
   }
   tsdf_engine::RcSet& o = e->rc[e->rc_cur];
   if (o.pending) { CU(cudaEventSynchronize(o.copied)); o.pending = false; }  // at most two views in flight
-  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, o.rgba, o.normal, o.depth, nullptr);
+  const size_t n = (size_t)w * h;
+  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, o.block, o.block + 4 * n, o.block + 8 * n, nullptr);
   if (rc) return rc;
   CU(cudaEventRecord(o.rendered, e->stream));
   CU(cudaStreamWaitEvent(e->d2h_stream, o.rendered, 0));
-  const size_t n = (size_t)w * h;
-  if (rgba) CU(cudaMemcpyAsync(rgba, o.rgba, 4 * n, cudaMemcpyDeviceToHost, e->d2h_stream));
-  if (normal) CU(cudaMemcpyAsync(normal, o.normal, 4 * n, cudaMemcpyDeviceToHost, e->d2h_stream));
-  if (hit_depth) CU(cudaMemcpyAsync(hit_depth, o.depth, 4 * n, cudaMemcpyDeviceToHost, e->d2h_stream));
+  CU(download_images(e, o.block, n, rgba, normal, hit_depth, e->d2h_stream));
   CU(cudaEventRecord(o.copied, e->d2h_stream));
   o.pending = true;  // the host waits for this copy before the set is rendered into again (two calls from now)
   e->rc_cur ^= 1;
@@ -492,12 +629,11 @@ int tsdf_raycast(tsdf_handle e, float max_depth, int w, int h, const float K[4],
   if (!e) return fail(TSDF_E_INVALID, "null engine handle");
   if ((int64_t)w * h > e->cfg.max_image_pixels) return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
   { int rcd = raycast_drain(e); if (rcd) return rcd; }
-  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, e->rgba, e->normal, e->hit_depth, nullptr);
-  if (rc) return rc;
   const size_t n = (size_t)w * h;
-  if (rgba) CU(cudaMemcpyAsync(rgba, e->rgba, 4 * n, cudaMemcpyDeviceToHost, e->stream));
-  if (normal) CU(cudaMemcpyAsync(normal, e->normal, 4 * n, cudaMemcpyDeviceToHost, e->stream));
-  if (hit_depth) CU(cudaMemcpyAsync(hit_depth, e->hit_depth, 4 * n, cudaMemcpyDeviceToHost, e->stream));
+  unsigned char* const blk = e->rc[0].block;
+  int rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, blk, blk + 4 * n, blk + 8 * n, nullptr);
+  if (rc) return rc;
+  CU(download_images(e, blk, n, rgba, normal, hit_depth, e->stream));
   CU(wait_stream(e, e->stream));
   return TSDF_OK;
 }
@@ -508,11 +644,13 @@ int tsdf_raycast_resident(tsdf_handle e, float max_depth, int w, int h, const fl
   if ((int64_t)w * h > e->cfg.max_image_pixels) return fail(TSDF_E_INVALID, "image %dx%d exceeds max_image_pixels=%d", w, h, e->cfg.max_image_pixels);
   int rc = raycast_drain(e);
   if (rc) return rc;
-  rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, e->rgba, e->normal, e->hit_depth, nullptr);
+  const size_t n = (size_t)w * h;
+  unsigned char* const blk = e->rc[0].block;
+  rc = tsdf_raycast_device(e, max_depth, w, h, K, q, t, blk, blk + 4 * n, blk + 8 * n, nullptr);
   if (rc) return rc;
-  if (d_rgba) *d_rgba = e->rgba;
-  if (d_normal) *d_normal = e->normal;
-  if (d_hit_depth) *d_hit_depth = e->hit_depth;
+  if (d_rgba) *d_rgba = blk;
+  if (d_normal) *d_normal = blk + 4 * n;
+  if (d_hit_depth) *d_hit_depth = blk + 8 * n;
   return TSDF_OK;
 }
 
@@ -867,6 +1005,7 @@ uint32_t tsdf_hash(int16_t bx, int16_t by, int16_t bz) { return hash_block(bx, b
 static int after_mutation(tsdf_engine* e) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(e->h_scalar, e->S.ctr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemsetAsync(e->S.ctr + C_PER_CALL, 0, sizeof(int) * (C_COUNT - C_PER_CALL), e->stream));  // frames expect them cleared
   CU(wait_stream(e, e->stream));
   e->n_active = e->cfg.pool_blocks - e->h_scalar[C_FREE];
   if (e->h_scalar[C_ERROR] & ERR_POOL) return fail(TSDF_E_POOL_EXHAUSTED, "voxel block pool exhausted (pool_blocks=%d)", e->cfg.pool_blocks);

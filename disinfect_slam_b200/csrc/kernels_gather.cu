@@ -170,7 +170,23 @@ __global__ void reinsert_kernel(DeviceState S) {
   }
 }
 
+// The per-frame counters go to the host through a store into mapped pinned memory, not through a copy engine: a
+// 128-byte cudaMemcpyAsync on the compute stream would queue behind the multi-megabyte image downloads of other
+// streams on the device-to-host engine and hold up every kernel enqueued after it.
+// The same kernel then clears the per-call counters for the next frame (a cudaMemsetAsync may also be serviced by a
+// copy engine).
+__global__ void publish_counters_kernel(int* __restrict__ ctr, volatile int* __restrict__ host) {
+  if (threadIdx.x < C_COUNT) {
+    host[threadIdx.x] = ctr[threadIdx.x];
+    if (threadIdx.x >= C_PER_CALL) ctr[threadIdx.x] = 0;
+  }
+  __threadfence_system();
+}
+
 // ---- launchers -------------------------------------------------------------------------------
+void launch_publish_counters(const DeviceState& S, int* host_mapped, cudaStream_t st) {
+  publish_counters_kernel<<<1, 32, 0, st>>>(S.ctr, host_mapped);
+}
 void launch_init_state(const DeviceState& S, cudaStream_t st) { init_state_kernel<<<1024, 256, 0, st>>>(S); }
 void launch_select_blocks(const DeviceState& S, bool use_bound, GridBound bound, int* selected, int num_sms,
                           cudaStream_t st) {

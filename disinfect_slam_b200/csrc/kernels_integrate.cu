@@ -24,12 +24,9 @@ namespace tsdf {
 //      8-corner visibility test and the CAS insert.
 // ------------------------------------------------------------------------------------------
 constexpr int kInlineSteps = 4;
-__global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, FrameParams P,
-                                                             const unsigned char* __restrict__ rgb,
-                                                             const float* __restrict__ depth,
-                                                             const float* __restrict__ ht,
-                                                             const float* __restrict__ lt,
+__global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, FrameParams P, FrameInput in,
                                                              Texel* __restrict__ tex) {
+  const unsigned char* __restrict__ rgb = in.rgb;
   // CTA = 32 x 8 pixels, warp = 8 x 4 pixels: the pixels of a warp fall into one or two blocks, so the
   // match.any de-duplication below leaves about one table probe per warp and DDA step
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -43,12 +40,25 @@ __global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, F
   float range = 1.f;
   bool valid = false;
   if (in_img) {
-    d = depth[idx];
+    // 16-bit sensor planes are converted here, with cv::Mat::convertTo's own arithmetic for CV_16U -> CV_32F
+    // (float(pixel) * float(scale), one rounding; examples/tsdf/offline.cc:77-80) -- no separate conversion pass
+    d = in.depth_u16 ? (float)static_cast<const unsigned short*>(in.depth)[idx] * in.depth_scale
+                     : static_cast<const float*>(in.depth)[idx];
     // K^-1 * (x, y, 1)  -- utils/tsdf/voxel_tsdf.cu:118-120
     pos_cam = kmul(P.Kinv, f3((float)x, (float)y, 1.f));
     range = sqrtf(sqnorm3(pos_cam));
     valid = !(d == 0 || d > P.max_depth);
-    const float dlogit = logf(ht[idx]) - logf(lt[idx]);
+    float p_ht = 1.f, p_lt = 1.f;  // no probability planes: TSDFSystem's default of ones (modules/tsdf_module.cc:28-33)
+    if (in.ht) {
+      if (in.prob_u16) {
+        p_ht = (float)static_cast<const unsigned short*>(in.ht)[idx] * in.prob_scale;
+        p_lt = (float)static_cast<const unsigned short*>(in.lt)[idx] * in.prob_scale;
+      } else {
+        p_ht = static_cast<const float*>(in.ht)[idx];
+        p_lt = static_cast<const float*>(in.lt)[idx];
+      }
+    }
+    const float dlogit = logf(p_ht) - logf(p_lt);
     const uint32_t rgbx = (uint32_t)rgb[3 * idx] | ((uint32_t)rgb[3 * idx + 1] << 8) | ((uint32_t)rgb[3 * idx + 2] << 16);
     *reinterpret_cast<uint4*>(tex + idx) =
         make_uint4(__float_as_uint(valid ? d : 0.f), __float_as_uint(range), __float_as_uint(dlogit), rgbx);
@@ -447,9 +457,8 @@ __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kerne
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const unsigned char* rgb, const float* depth,
-                           const float* ht, const float* lt, Texel* tex, cudaStream_t st) {
-  frame_allocate_kernel<<<dim3((P.w + 31) / 32, (P.h + 7) / 8), 256, 0, st>>>(S, P, rgb, depth, ht, lt, tex);
+void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const FrameInput& in, Texel* tex, cudaStream_t st) {
+  frame_allocate_kernel<<<dim3((P.w + 31) / 32, (P.h + 7) / 8), 256, 0, st>>>(S, P, in, tex);
 }
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int* vis_state, int num_sms, cudaStream_t st) {
   select_visible_kernel<<<num_sms * 4, 256, 0, st>>>(S, P, visible, vis_state);

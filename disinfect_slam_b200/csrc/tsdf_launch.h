@@ -7,8 +7,7 @@
 namespace tsdf {
 
 // kernels_integrate.cu
-void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const unsigned char* rgb, const float* depth,
-                           const float* ht, const float* lt, Texel* tex, cudaStream_t st);
+void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const FrameInput& in, Texel* tex, cudaStream_t st);
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int* vis_state, int num_sms,
                            cudaStream_t st);
 void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
@@ -39,6 +38,7 @@ void launch_retrieve_list(const DeviceState& S, const short* points, int n, floa
 void launch_assign_list(const DeviceState& S, const short* points, int n, const float* tsdf, const unsigned* rgbw,
                         const float* prob, cudaStream_t st);
 void launch_rehash(const DeviceState& S, int num_sms, cudaStream_t st);
+void launch_publish_counters(const DeviceState& S, int* host_mapped, cudaStream_t st);
 
 // kernels_mesh.cu
 void launch_mesh_count(const DeviceState& S, const int* selected, int n_selected, float voxel_size, unsigned long long* counter,

@@ -8,8 +8,8 @@ drive the engine and volumes can be dumped the way the reference does:
   <logdir>/<id>_ht.png, _no_ht.png  16-bit probabilities, value / 65535; absent -> ht = 0, lt = 1 (offline.cc:74-83)
   /tmp/data.bin-style dump        raw VoxelSpatialTSDF records {float x, y, z, tsdf} (offline.cc:184-190)
 
-Pure host code (numpy + cv2 for PNG I/O).  The pixel conversions mirror cv::Mat::convertTo (double scale factor,
-result rounded to float32); the rotation-matrix -> quaternion conversion mirrors Eigen 3.3's
+Pure host code (numpy + cv2 for PNG I/O).  The pixel conversions mirror cv::Mat::convertTo of a 16-bit image (float32
+pixel times the scale factor cast to float32); the rotation-matrix -> quaternion conversion mirrors Eigen 3.3's
 QuaternionBase::operator=(Matrix3) in float32, which is what SE3<float>(Matrix<float,3,4>) runs
 (utils/cuda/lie_group.cuh:19-20).
 """
@@ -115,9 +115,16 @@ def read_trajectory(logdir, extrinsics=None):
     return out
 
 
+def convert_scale(scale):
+    """The factor cv::Mat::convertTo(CV_32FC1, scale) really multiplies by: for a 16-bit source OpenCV's cvtScale works
+    in float32 -- the double `scale` is cast to float once (modules/core/src/convert_scale.simd.hpp, wtype = float;
+    verified against cv2 4.13 on all 65536 inputs, tests/test_replay_formats.py)."""
+    return np.float32(scale)
+
+
 def _convert(img_u16, scale):
-    """cv::Mat::convertTo(CV_32FC1, scale): double multiply, rounded to float32."""
-    return (img_u16.astype(np.float64) * scale).astype(np.float32)
+    """cv::Mat::convertTo(CV_32FC1, scale) of a CV_16UC1 image: float32(pixel) * float32(scale), one rounding."""
+    return img_u16.astype(np.float32) * convert_scale(scale)
 
 
 def read_frame(logdir, frame_id, depthmap_factor):

@@ -126,6 +126,21 @@ class TSDFGrid:
         fn = self.L.tsdf_integrate_async if asynchronous else self.L.tsdf_integrate
         check(fn(self.h, _p(img_rgb), _p(img_depth), _p(img_ht), _p(img_lt), w, h, max_depth, _p(K), _p(q), _p(t)))
 
+    def IntegrateU16(self, img_rgb, depth_u16, ht_u16, lt_u16, depthmap_factor, max_depth, intrinsics, cam_T_world, flags=0):
+        """The sensor's own formats (tsdf_integrate_u16): uint16 depth (metres = value / depthmap_factor) and uint16
+        probabilities (value / 65535; both None = planes of ones), converted on the GPU with cv::Mat::convertTo's
+        arithmetic.  flags: 0 synchronous, 1 = TSDF_FRAME_ASYNC, 2 = TSDF_FRAME_NOWAIT."""
+        h, w = depth_u16.shape
+        if img_rgb.dtype != np.uint8 or img_rgb.shape != (h, w, 3) or depth_u16.dtype != np.uint16:
+            raise ValueError("rgb must be uint8 HxWx3, depth uint16 HxW")
+        for a in (ht_u16, lt_u16):
+            if a is not None and (a.dtype != np.uint16 or a.shape != (h, w)):
+                raise ValueError("ht / lt must be uint16 HxW or None")
+        q, t = _pose(cam_T_world)
+        K = _f32(intrinsics, 4)
+        check(self.L.tsdf_integrate_u16(self.h, _p(img_rgb), _p(depth_u16), _p(ht_u16), _p(lt_u16), w, h, depthmap_factor, max_depth,
+                                        _p(K), _p(q), _p(t), int(flags)))
+
     def IntegrateDevice(self, d_rgb, d_depth, d_ht, d_lt, width, height, max_depth, intrinsics, cam_T_world,
                         after_event=None):
         """Planes already in device memory (raw device pointers as ints)."""
@@ -334,3 +349,68 @@ class TSDFGrid:
         if nb:
             check(self.L.tsdf_export_blocks(self.h, _p(keys), _p(tsdf), _p(rgbw), _p(prob), nb, C.byref(n)))
         return keys, tsdf, rgbw, prob
+
+
+def packed_pinned_frame(rgb, depth, ht=None, lt=None):
+    """One pinned block holding the planes of a frame back to back -- [rgb | depth | ht | lt] -- and views of the planes in
+    it.  The engine recognises this layout and uploads the frame with ONE DMA transfer (large transfers keep the PCIe
+    link much busier than four small ones when image downloads run at the same time).  Returns (PinnedArray, dict of
+    views); keep the PinnedArray alive as long as the views are used."""
+    parts = [np.ascontiguousarray(rgb), np.ascontiguousarray(depth)] + ([np.ascontiguousarray(ht), np.ascontiguousarray(lt)] if ht is not None else [])
+    block = PinnedArray((sum(a.nbytes for a in parts),), np.uint8)
+    views, off = [], 0
+    for a in parts:
+        v = block.array[off:off + a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        views.append(v)
+        off += a.nbytes
+    d = dict(rgb=views[0], depth=views[1], ht=views[2] if ht is not None else None, lt=views[3] if ht is not None else None)
+    return block, d
+
+
+def packed_pinned_images(height, width, n_sets, with_depth=False):
+    """n_sets pinned blocks [rgba | normal (| hit depth)] -- adjacent host images are downloaded with one transfer.
+    Returns (blocks, rgba views, normal views, depth views or None)."""
+    n = height * width
+    blocks = [PinnedArray(((12 if with_depth else 8) * n,), np.uint8) for _ in range(n_sets)]
+    rgba = [b.array[:4 * n].reshape(height, width, 4) for b in blocks]
+    normal = [b.array[4 * n:8 * n].reshape(height, width, 4) for b in blocks]
+    depth = [b.array[8 * n:].view(np.float32).reshape(height, width) for b in blocks] if with_depth else None
+    return blocks, rgba, normal, depth
+
+
+def make_host_frames(per_stream):
+    """ctypes array of tsdf_host_frame, stream-major, for run_streams.  per_stream: list (streams) of lists (frames) of
+    dicts with rgb / depth / ht / lt (pinned numpy views; ht / lt may be None), q, t; uint16 depth selects the 16-bit format."""
+    n_frames = len(per_stream[0])
+    arr = (_lib.HostFrame * (len(per_stream) * n_frames))()
+    for b, frames in enumerate(per_stream):
+        assert len(frames) == n_frames
+        for i, f in enumerate(frames):
+            x = arr[b * n_frames + i]
+            x.rgb, x.depth = f["rgb"].ctypes.data, f["depth"].ctypes.data
+            x.ht = None if f.get("ht") is None else f["ht"].ctypes.data
+            x.lt = None if f.get("lt") is None else f["lt"].ctypes.data
+            x.q[:] = [float(v) for v in f["q"]]
+            x.t[:] = [float(v) for v in f["t"]]
+            x.format = 1 if f["depth"].dtype == np.uint16 else 0
+    return arr
+
+
+def run_streams(grids, frames, first, count, width, height, max_depth, intrinsics, depthmap_factor=1.0, raycast=True, rgba=None,
+                normal=None, hit_depth=None):
+    """tsdf_streams_run: the calling thread drives all `grids` (one engine per stream).  rgba / normal / hit_depth: lists of
+    2 * len(grids) pinned arrays (two image sets per stream) or None for images that are not downloaded."""
+    L = _lib.lib()
+    n = len(grids)
+    eng = (C.c_void_p * n)(*[g.h for g in grids])
+    K = _f32(intrinsics, 4)
+
+    def ptrs(lst):
+        if lst is None:
+            return None
+        assert len(lst) == 2 * n
+        return (C.c_void_p * (2 * n))(*[a.ctypes.data for a in lst])
+
+    check(L.tsdf_streams_run(n, eng, frames, len(frames) // n, first, count, width, height, depthmap_factor, max_depth, _p(K), int(raycast),
+                             ptrs(rgba), ptrs(normal), ptrs(hit_depth)))

@@ -101,6 +101,45 @@ int tsdf_integrate(tsdf_handle h, const uint8_t* rgb, const float* depth, const 
 int tsdf_integrate_async(tsdf_handle h, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
                          int width, int height, float max_depth, const float K[4], const float q_xyzw[4],
                          const float t_xyz[3]);
+/* tsdf_integrate_async without the wait for the upload: returns as soon as everything is enqueued (no host wait at all
+ * unless the frame two calls back is still running).  The host buffers must be pinned (tsdf_host_alloc) and stay
+ * untouched until two further frames have been submitted or tsdf_synchronize() has returned.  ht == lt == NULL: no
+ * probability planes (= planes of ones, TSDFSystem's default, modules/tsdf_module.cc:28-33), nothing is uploaded
+ * for them.  This is the call a host thread that drives several engines (streams) uses. */
+int tsdf_integrate_enqueue(tsdf_handle h, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
+                           int width, int height, float max_depth, const float K[4], const float q_xyzw[4],
+                           const float t_xyz[3]);
+/* The sensor's own formats: 16-bit depth (metres = value / depthmap_factor) and 16-bit probabilities (value / 65535),
+ * as the reference reads them from a log or a camera before `convertTo(CV_32FC1, 1. / scale)`
+ * (examples/tsdf/offline.cc:72-83, cameras/l515.cc:24-31).  9 bytes per pixel cross PCIe instead of 15 (5 with
+ * ht == lt == NULL); the conversion runs inside the allocation kernel with convertTo's arithmetic for CV_16U
+ * (float32 pixel * float32 factor), so the volume is bit-identical to converting on the host and calling
+ * tsdf_integrate.  flags: 0 = synchronous like tsdf_integrate, TSDF_FRAME_ASYNC = like tsdf_integrate_async,
+ * TSDF_FRAME_NOWAIT = like tsdf_integrate_enqueue. */
+#define TSDF_FRAME_ASYNC 1
+#define TSDF_FRAME_NOWAIT 2
+int tsdf_integrate_u16(tsdf_handle h, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht, const uint16_t* lt,
+                       int width, int height, float depthmap_factor, float max_depth, const float K[4],
+                       const float q_xyzw[4], const float t_xyz[3], int flags);
+/* Several independent engines (streams) of one GPU driven by the calling thread alone: for i in [first, first + count)
+ * and every stream b, frame = frames[b * n_frames + i % n_frames] goes through tsdf_integrate_enqueue (or
+ * tsdf_integrate_u16 with TSDF_FRAME_NOWAIT, per frame format) and, if raycast != 0, through tsdf_raycast_async from
+ * the frame's camera into host image set 2 * b + (i & 1) (each of rgba / normal / hit_depth may be NULL: that
+ * image is not downloaded; TSDFGrid::RayCast itself delivers rgba + normal); the images of step i - 1 are waited for
+ * during step i, every engine is synchronised at the end.  All host memory must be pinned.  This replaces one
+ * blocking host thread per stream (what a TSDFSystem worker is, modules/tsdf_module.cc:51-75) where many streams
+ * share a host. */
+#define TSDF_FORMAT_F32 0
+#define TSDF_FORMAT_U16 1
+typedef struct tsdf_host_frame {
+  const void *rgb, *depth, *ht, *lt; /* pinned host memory; ht == lt == NULL: no probability planes */
+  float q_xyzw[4];
+  float t_xyz[3];
+  int32_t format; /* TSDF_FORMAT_F32: float32 depth / ht / lt; TSDF_FORMAT_U16: uint16 planes */
+} tsdf_host_frame;
+int tsdf_streams_run(int n_streams, const tsdf_handle* engines, const tsdf_host_frame* frames, int n_frames, int first,
+                     int count, int width, int height, float depthmap_factor, float max_depth, const float K[4],
+                     int raycast, uint8_t* const* rgba, uint8_t* const* normal, float* const* hit_depth);
 /* Same, with the four planes already in device memory of the engine's GPU (SURVEY.md 8f rank 4:
  * the segmentation net produces ht/lt on the GPU; multi-GPU ranks receive the broadcast frame
  * in device memory).  Enqueues on the engine stream and returns without synchronising;

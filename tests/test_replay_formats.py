@@ -31,7 +31,7 @@ def test_log_round_trip(tmp_path):
         assert np.array_equal(g["rgb"], f["rgb"])
         # synthetic depth is already quantised to 1 / depth_factor: the 16-bit round trip is the convertTo rule
         d16 = np.rint(f["depth"].astype(np.float64) * cfg.depth_factor)
-        assert np.array_equal(g["depth"], (d16 * (1.0 / cfg.depth_factor)).astype(np.float32))
+        assert np.array_equal(g["depth"], d16.astype(np.float32) * np.float32(1.0 / cfg.depth_factor))
         assert np.abs(g["depth"] - f["depth"]).max() < 1e-6
         assert np.abs(g["ht"] - f["ht"]).max() <= 0.5 / 65535 + 1e-7 and g["ht"].dtype == np.float32
         assert min(np.abs(g["q"] - f["q"]).max(), np.abs(g["q"] + f["q"]).max()) < 1e-6 and np.abs(g["t"] - f["t"]).max() < 1e-6
@@ -79,6 +79,17 @@ def test_trajectory_extrinsics_premultiply(tmp_path):
     # frames carry the composed pose
     f = next(replay.read_log(str(tmp_path), cfg.depth_factor, L515_EXTRINSICS))
     assert np.array_equal(f["q"], ext[0][1]) and np.array_equal(f["t"], ext[0][2])
+
+
+def test_convert_rule_equals_opencv_on_every_16_bit_value():
+    """cv::Mat::convertTo(CV_32FC1, 1. / scale) for CV_16UC1 (examples/tsdf/offline.cc:77-80) multiplies in float32; cv2
+    exposes the same cvtScale kernel through normalize(NORM_MINMAX), whose scale factor is known in closed form."""
+    import cv2
+    src = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    beta = 65535.0 / 5000.0
+    got = cv2.normalize(src, None, alpha=0.0, beta=beta, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_32F)
+    assert np.array_equal(got, replay._convert(src, beta / 65535.0))
+    assert not np.array_equal(got, (src.astype(np.float64) * (beta / 65535.0)).astype(np.float32))  # the double rule is NOT it
 
 
 def test_tsdf_dump_records(tmp_path):
