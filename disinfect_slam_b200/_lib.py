@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsdf_b200.so")
+LIB_PATH = os.environ.get("TSDF_B200_LIB") or os.path.join(_HERE, "libtsdf_b200.so")  # the override is for kernel experiments (tools/kbench.py)
 CSRC = os.path.join(_HERE, "csrc")
 _LIB = None
 

@@ -315,7 +315,9 @@ int tsdf_create(float voxel_size, float truncation, const tsdf_config* user_cfg,
   CUX(cudaMalloc(&e->skip.dist, kSkipMaxCells)); CUX(cudaMalloc(&e->skip.scratch, kSkipMaxCells));
   CUX(cudaMalloc(&e->skip.hdr, sizeof(int) * kSkipHdrInts));
   CUX(cudaMemsetAsync(e->skip.hdr, 0, sizeof(int) * kSkipHdrInts, e->stream));
-  CUX(cudaMalloc(&e->skip.index, sizeof(int) * (size_t)kSkipMaxCells));
+  CUX(cudaMalloc(&e->skip.cells, sizeof(int) * (size_t)kSkipMaxCells));
+  // both byte planes start entirely at the cap: the rebuild kernels keep the plane they will mark next in that state
+  CUX(cudaMemsetAsync(e->skip.dist, kSkipCap, kSkipMaxCells, e->stream)); CUX(cudaMemsetAsync(e->skip.scratch, kSkipCap, kSkipMaxCells, e->stream));
   const size_t npx = (size_t)cfg.max_image_pixels;
   for (int i = 0; i < 2; ++i) {
     FrameBuf& f = e->fb[i];
@@ -349,7 +351,7 @@ int tsdf_destroy(tsdf_handle e) {
   for (int i = 0; i < 2; ++i) { if (e->rc[i].rendered) cudaEventDestroy(e->rc[i].rendered); if (e->rc[i].copied) cudaEventDestroy(e->rc[i].copied); }
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
   cudaFree(e->visible); cudaFree(e->selected); cudaFree(e->mesh_out); cudaFree(e->mesh_counter);
-  cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr); cudaFree(e->skip.index);
+  cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr); cudaFree(e->skip.cells);
   for (int r = 0; r < kMaxPeers; ++r) for (int k = 0; k < 4; ++k) if (e->ipc_opened[r][k]) cudaIpcCloseMemHandle(e->ipc_opened[r][k]);
   cudaFree(e->d_self); cudaFree(e->d_peers);
   for (int i = 0; i < 2; ++i) {

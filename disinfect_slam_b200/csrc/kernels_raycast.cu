@@ -25,16 +25,30 @@ namespace tsdf {
 // ------------------------------------------------------------------------------------------
 // skip-map construction (all sizes live on the device: no host round trip)
 // ------------------------------------------------------------------------------------------
-// header from the AABB counters + fill with the cap.  Every thread derives the same header (a handful of integer
-// operations) so that no separate one-thread launch is needed; thread 0 publishes it for the later kernels.
+// Four launches: mark, then the three separable passes of the capped Chebyshev transform.
+//
 // Build attempts are numbered (gen) by the host.  With `lazy` set, attempt g first compares the serial of the last call
 // that changed each shard's block set (ctr[C_DIRTY], written on NET changes only, see mark_block_set_changed; read
 // over NVLink for foreign shards) with the serials recorded by attempt g - 1: all equal means the map is still exact
-// and all five kernels return at once -- a frame that neither allocated nor carved a surviving block (a static
-// camera, a converged scene), or a batch of views over a finished volume, costs five empty launches instead of a
+// and all four kernels return at once -- a frame that neither allocated nor carved a surviving block (a static
+// camera, a converged scene), or a batch of views over a finished volume, costs four empty launches instead of a
 // rebuild.  The records of consecutive attempts alternate between two halves of the header, so that no thread reads
-// a word another thread of the same kernel writes; the verdict for the four later kernels goes to hdr[10 + (g & 1)].
-__global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M, int gen, int lazy) {
+// a word another thread of the same kernel writes; the verdict for the later kernels goes to hdr[10 + (g & 1)].
+//
+// No fill pass: the two byte planes swap roles at every rebuild, and the plane the NEXT rebuild will mark into is
+// always entirely at the cap -- it is filled once at creation, and the last pass of every rebuild restores the cells
+// it had dirtied (the plane is idle by then).  hdr[8 + (g & 1)] = number of rebuilds after attempt g; its parity
+// before the attempt tells every kernel which plane plays which role.
+struct Planes { unsigned char* mark; unsigned char* other; };
+__device__ __forceinline__ Planes planes_of(const SkipMap& M, int gen) {
+  const bool odd = M.hdr[8 + ((gen - 1) & 1)] & 1;
+  Planes p; p.mark = odd ? M.scratch : M.dist; p.other = odd ? M.dist : M.scratch;
+  return p;
+}
+
+// Every thread derives the same header from the AABB counters (a handful of integer operations), so that no separate
+// one-thread launch is needed; thread 0 publishes it for the later kernels.
+__global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M, int gen, int lazy) {
   {
     int* const now = M.hdr + kSkipSigBase + (gen & 1) * kSkipSigInts;
     const int* const before = M.hdr + kSkipSigBase + ((gen - 1) & 1) * kSkipSigInts;
@@ -44,6 +58,7 @@ __global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restri
       now[0] = n_shards;
       for (int r = 0; r < n_shards; ++r) now[1 + r] = shards[r].ctr[C_DIRTY];
       M.hdr[10 + (gen & 1)] = rebuild ? 1 : 0;
+      M.hdr[8 + (gen & 1)] = M.hdr[8 + ((gen - 1) & 1)] + (rebuild ? 1 : 0);
       if (rebuild) M.hdr[12]++;
     }
     if (!rebuild) return;
@@ -67,22 +82,11 @@ __global__ void __launch_bounds__(256) skip_fill_kernel(const PeerView* __restri
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     int* h = M.hdr;
+    h[13] = h[7];  // cells the previous rebuild dirtied in the plane this one restores (the layout may have shrunk: larger shift)
     h[0] = n ? x0 : 0; h[1] = n ? y0 : 0; h[2] = n ? z0 : 0; h[3] = (int)nx; h[4] = (int)ny; h[5] = (int)nz; h[6] = shift; h[7] = n;
   }
-  // 16 bytes per store; the buffer is kSkipMaxCells long, so rounding n up to a multiple of 16 stays inside
-  const uint4 cap16 = make_uint4(0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap, 0x01010101u * kSkipCap);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 15) / 16; i += gridDim.x * blockDim.x)
-    reinterpret_cast<uint4*>(M.dist)[i] = cap16;
-  if (shift == 0) {  // one cell = one block: a dense block index (owner shard << kIndexShardShift | pool index) beside the distances
-    const int4 none = make_int4(-1, -1, -1, -1);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 3) / 4; i += gridDim.x * blockDim.x)
-      reinterpret_cast<int4*>(M.index)[i] = none;
-  }
-}
-
-__global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M, int gen) {
-  if (!M.hdr[10 + (gen & 1)]) return;
-  const int ox = M.hdr[0], oy = M.hdr[1], oz = M.hdr[2], nx = M.hdr[3], ny = M.hdr[4], shift = M.hdr[6];
+  if (n == 0) return;
+  unsigned char* const plane = planes_of(M, gen).mark;  // all cells at the cap (see above)
   for (int r = 0; r < n_shards; ++r) {
     const int hw = shards[r].ctr[C_HIGH_WATER];
     const u64* dir = shards[r].block_key;
@@ -90,10 +94,12 @@ __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restri
       const u64 k = dir[i];
       if (k == kEmpty) continue;
       int bx, by, bz; unpack_key(k, bx, by, bz);
-      const int cx = (bx - ox) >> shift, cy = (by - oy) >> shift, cz = (bz - oz) >> shift;
+      const int cx = (bx - x0) >> shift, cy = (by - y0) >> shift, cz = (bz - z0) >> shift;
       const size_t cell = ((size_t)cz * ny + cy) * nx + cx;
-      M.dist[cell] = 0;
-      if (shift == 0) M.index[cell] = (r << kIndexShardShift) | i;  // directory position = pool index
+      plane[cell] = 0;
+      // occupied cell: >= 0.  One cell = one block (shift 0): owner shard << kIndexShardShift | pool index (the directory
+      // position IS the pool index), so the ray caster needs no table probe; coarser cells: 0, the caster probes the table
+      M.cells[cell] = shift == 0 ? ((r << kIndexShardShift) | i) : 0;
     }
   }
 }
@@ -101,10 +107,15 @@ __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restri
 // one separable pass of the capped Chebyshev distance transform along AXIS:
 //   out(c) = min_k max(in(c +- k e_axis), k),  k < cap
 // All 2 * (cap - 1) neighbour reads of a cell are independent (no early exit), so they are in flight together.
+// Plane roles: pass 0 reads the marked plane and writes the other, pass 1 goes back, pass 2 reads the marked plane again
+// and writes the merged grid the ray caster reads with ONE load per sample -- empty cells get -distance, occupied cells
+// keep the entry the mark kernel wrote -- and puts the other plane (idle by now) back to the cap for the next rebuild.
 template <int AXIS>
-__global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigned char* __restrict__ in,
-                                                        unsigned char* __restrict__ out, int gen) {
+__global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, int gen) {
   if (!M.hdr[10 + (gen & 1)]) return;
+  const Planes P = planes_of(M, gen);
+  const unsigned char* __restrict__ in = AXIS == 1 ? P.other : P.mark;
+  unsigned char* __restrict__ out = AXIS == 1 ? P.mark : P.other;
   const int nx = M.hdr[3], ny = M.hdr[4], nz = M.hdr[5], n = M.hdr[7];
   const int len = AXIS == 0 ? nx : AXIS == 1 ? ny : nz;
   const int stride = AXIS == 0 ? 1 : AXIS == 1 ? nx : nx * ny;
@@ -119,46 +130,45 @@ __global__ void __launch_bounds__(256) skip_pass_kernel(SkipMap M, const unsigne
         best = min(best, max(min(lo, hi), k));
       }
     }
-    out[i] = (unsigned char)best;
+    if (AXIS == 2) { if (best > 0) M.cells[i] = -best; out[i] = (unsigned char)kSkipCap; }
+    else out[i] = (unsigned char)best;
   }
+  if (AXIS == 2)  // the plane being restored was the previous rebuild's marked plane: dirty up to THAT rebuild's cell count
+    for (int i = n + blockIdx.x * blockDim.x + threadIdx.x; i < M.hdr[13]; i += gridDim.x * blockDim.x) out[i] = (unsigned char)kSkipCap;
 }
 
 void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int gen, bool lazy, int num_sms, cudaStream_t st) {
-  skip_fill_kernel<<<num_sms * 4, 256, 0, st>>>(shards, n_shards, M, gen, lazy ? 1 : 0);
-  skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(shards, n_shards, M, gen);
-  skip_pass_kernel<0><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, gen);
-  skip_pass_kernel<1><<<num_sms * 8, 256, 0, st>>>(M, M.scratch, M.dist, gen);
-  skip_pass_kernel<2><<<num_sms * 8, 256, 0, st>>>(M, M.dist, M.scratch, gen);
-  // result is in M.scratch; the raycast kernel is launched with the two pointers swapped
+  skip_mark_kernel<<<num_sms * 2, 256, 0, st>>>(shards, n_shards, M, gen, lazy ? 1 : 0);
+  skip_pass_kernel<0><<<num_sms * 8, 256, 0, st>>>(M, gen);
+  skip_pass_kernel<1><<<num_sms * 8, 256, 0, st>>>(M, gen);
+  skip_pass_kernel<2><<<num_sms * 8, 256, 0, st>>>(M, gen);
 }
 
 // ------------------------------------------------------------------------------------------
 // ray march
 // ------------------------------------------------------------------------------------------
-struct Grid { int ox, oy, oz, nx, ny, nz, shift; const unsigned char* dist; const int* index; };
+struct Grid { int ox, oy, oz, nx, ny, nz, shift; const int* cells; };
 struct BlockCache { int bx, by, bz; const unsigned char* base; };  // bx = INT_MIN: nothing cached; base = null: absent
 
 // Where the voxels of a block live.  Local: this engine's table and pool.  Shared: the table and pool of the shard
 // that owns the block coordinate (owner_of), reached through peer-mapped pointers -- NVLink loads inside the march.
 template <bool SHARED> struct Volume;
 template <> struct Volume<false> {
-  static constexpr bool kDenseIndex = true;
   DeviceState S;
-  __device__ __forceinline__ const unsigned char* at(int idx) const { return idx < 0 ? nullptr : S.voxels + (size_t)idx * kBlockBytes; }
+  __device__ __forceinline__ const unsigned char* at(int entry) const { return S.voxels + (size_t)entry * kBlockBytes; }
   __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
     const int idx = table_find(S, pack_key(bx, by, bz));
     return idx < 0 ? nullptr : S.voxels + (size_t)idx * kBlockBytes;
   }
 };
 template <> struct Volume<true> {
-  static constexpr bool kDenseIndex = true;
   const PeerView* shards; int n_shards, shard_shift;
   // Fused exchange of the results: when n_out > 0 every ray's pixel is stored into the image buffers of ALL ranks
   // (peer-mapped pointers, posted stores over NVLink issued as the rays finish) instead of into one local image that an
   // all-gather would have to distribute afterwards.
   int n_out; uchar4* out_rgba[kMaxPeers]; uchar4* out_normal[kMaxPeers]; float* out_depth[kMaxPeers];
-  __device__ __forceinline__ const unsigned char* at(int idx) const {  // owner shard in the top bits: no table probe over NVLink
-    return idx < 0 ? nullptr : shards[idx >> kIndexShardShift].voxels + (size_t)(idx & ((1 << kIndexShardShift) - 1)) * kBlockBytes;
+  __device__ __forceinline__ const unsigned char* at(int entry) const {  // owner shard in the top bits: no table probe over NVLink
+    return shards[entry >> kIndexShardShift].voxels + (size_t)(entry & ((1 << kIndexShardShift) - 1)) * kBlockBytes;
   }
   __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
     const u64 key = pack_key(bx, by, bz);
@@ -171,17 +181,22 @@ __device__ __forceinline__ const float* base_tsdf(const unsigned char* b) { retu
 __device__ __forceinline__ const uint32_t* base_rgbw(const unsigned char* b) { return reinterpret_cast<const uint32_t*>(b + kPlaneBytes); }
 __device__ __forceinline__ const float* base_logit(const unsigned char* b) { return reinterpret_cast<const float*>(b + 2 * kPlaneBytes); }
 
-// Chebyshev distance (cells) from block (bx,by,bz) to the nearest cell holding an active block;
-// 0 = this cell holds one (the block itself may still be absent when shift > 0)
+// What the map says about block (bx, by, bz):
+//   >= 0       its cell holds an active block (the value is the dense index entry when one cell is one block)
+//   -d         the nearest cell holding a block is at least d cells away (Chebyshev); every cell closer is empty
+//   kEscaped   the ray can never meet a block again
 // `leaving`: bit a = the ray does not increase along axis a, bit 3 + a = it does not decrease.  A sample outside the
 // AABB on a side the ray is moving away from (or along) can never be followed by a sample inside it -- the accumulated
-// position is monotonic per axis and no block exists outside the AABB -- so the ray is a miss: kEscaped is returned.
-constexpr int kEscaped = 1 << 30;
-__device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int bz, int& cell, unsigned leaving = 0u) {
-  const int cx = (bx - G.ox) >> G.shift, cy = (by - G.oy) >> G.shift, cz = (bz - G.oz) >> G.shift;
+// position is monotonic per axis and no block exists outside the AABB -- so the ray is a miss.
+constexpr int kEscaped = (int)0x80000000;
+// DENSE: one cell = one block (shift 0), the usual case; the march kernel branches once, uniformly, into the
+// instantiation that knows it (no shifts, no table probes in its code)
+template <bool DENSE>
+__device__ __forceinline__ int cell_value(const Grid& G, int bx, int by, int bz, unsigned leaving = 0u) {
+  const int sh = DENSE ? 0 : G.shift;
+  const int cx = (bx - G.ox) >> sh, cy = (by - G.oy) >> sh, cz = (bz - G.oz) >> sh;
   if ((unsigned)cx < (unsigned)G.nx && (unsigned)cy < (unsigned)G.ny && (unsigned)cz < (unsigned)G.nz) {
-    cell = (cz * G.ny + cy) * G.nx + cx;  // at most 2^22 cells
-    return __ldg(G.dist + cell);
+    return __ldg(G.cells + (unsigned)((cz * G.ny + cy) * G.nx + cx));  // at most 2^22 cells
   }
   const unsigned below = (cx < 0 ? 1u : 0u) | (cy < 0 ? 2u : 0u) | (cz < 0 ? 4u : 0u);
   const unsigned above = (cx >= G.nx ? 8u : 0u) | (cy >= G.ny ? 16u : 0u) | (cz >= G.nz ? 32u : 0u);
@@ -190,7 +205,7 @@ __device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int 
   const int gx = cx < 0 ? -cx : (cx >= G.nx ? cx - G.nx + 1 : 0);
   const int gy = cy < 0 ? -cy : (cy >= G.ny ? cy - G.ny + 1 : 0);
   const int gz = cz < 0 ? -cz : (cz >= G.nz ? cz - G.nz + 1 : 0);
-  return max(gx, max(gy, gz));
+  return -max(gx, max(gy, gz));
 }
 
 // nearest voxel of a grid position: roundf + the reference's saturating float -> short cast.  CLAMP = false is chosen on
@@ -199,17 +214,16 @@ __device__ __forceinline__ int cell_distance(const Grid& G, int bx, int by, int 
 template <bool CLAMP>
 __device__ __forceinline__ int nearest_voxel(float f) { return CLAMP ? round_to_voxel(f) : __float2int_rz(roundf(f)); }
 
-// voxels of block (bx, by, bz), whose cell holds an active block (distance 0): straight from the dense index when one cell
-// is one block of this engine (the usual case), through the owner's hash table otherwise
-template <class V>
-__device__ __forceinline__ const unsigned char* block_in_cell(const V& vol, const Grid& G, int cell, int bx, int by, int bz) {
-  if (V::kDenseIndex && G.shift == 0) return vol.at(__ldg(G.index + cell));
-  return vol.find(bx, by, bz);
+// voxels of block (bx, by, bz) or null: straight from the dense entry when one cell is one block (the usual case),
+// through the owner's hash table otherwise
+template <bool DENSE, class V>
+__device__ __forceinline__ const unsigned char* block_of(const V& vol, const Grid& G, int g, int bx, int by, int bz) {
+  return DENSE ? vol.at(g) : vol.find(bx, by, bz);
 }
 template <class V>
 __device__ __forceinline__ const unsigned char* block_or_null(const V& vol, const Grid& G, int bx, int by, int bz) {
-  int cell = 0;
-  return cell_distance(G, bx, by, bz, cell) == 0 ? block_in_cell(vol, G, cell, bx, by, bz) : nullptr;
+  if (G.shift == 0) { const int g = cell_value<true>(G, bx, by, bz); return g >= 0 ? vol.at(g) : nullptr; }
+  return cell_value<false>(G, bx, by, bz) >= 0 ? vol.find(bx, by, bz) : nullptr;
 }
 
 template <class V>
@@ -236,27 +250,61 @@ __device__ __forceinline__ float fetch_tsdf_f(const V& vol, const Grid& G, Block
 // guaranteed to land in unallocated space.  With d = distance of p's cell and cs voxels per cell,
 // every voxel within Chebyshev radius (d-1)*cs of p is unallocated; m further steps move the rounded
 // voxel by at most m*smax + 1 (+1 slack for float accumulation), so m = floor(((d-1)*cs - 2) / smax).
-template <bool CLAMP, class V>
-__device__ __forceinline__ float march_sample(const V& vol, const Grid& G, BlockCache& c, float3 p, float inv_smax, unsigned leaving,
-                                              int& skip) {
+// No per-lane block cache here: with steps of 3 voxels and blocks of 8 some lane of a warp changes block in 93 % of
+// the rounds (ncu), so the warp took the look-up path anyway -- and a cache updated on divergent paths cost more
+// register shuffling than the load it saved.  The map cell is loaded every sample (L1-resident, 4 bytes).
+template <bool CLAMP, bool DENSE, class V>
+__device__ __forceinline__ float march_sample(const V& vol, const Grid& G, float3 p, float inv_smax, unsigned leaving, int& skip) {
   const int px = nearest_voxel<CLAMP>(p.x), py = nearest_voxel<CLAMP>(p.y), pz = nearest_voxel<CLAMP>(p.z);
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
+  const int g = cell_value<DENSE>(G, bx, by, bz, leaving);
   skip = 0;
-  if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
-    c.bx = bx; c.by = by; c.bz = bz;
-    int cell = 0;
-    const int d = cell_distance(G, bx, by, bz, cell, leaving);
-    if (d == 0) {
-      c.base = block_in_cell(vol, G, cell, bx, by, bz);
-    } else {
-      c.base = nullptr;
-      if (d == kEscaped) skip = kEscaped;  // the ray has left the volume for good
-      else if (d >= 2) skip = __float2int_rd((float)(((d - 1) << (3 + G.shift)) - 2) * inv_smax);
-      return 1.f;
-    }
+  float t = 1.f;
+  if (g >= 0) {
+    const unsigned char* base = block_of<DENSE>(vol, G, g, bx, by, bz);
+    if (DENSE || base) t = __ldg(base_tsdf(base) + voxel_index(px, py, pz));
+  } else if (g == kEscaped) {
+    skip = kEscaped;  // the ray has left the volume for good
+  } else if (g <= -2) {
+    skip = __float2int_rd((float)(((-g - 1) << (DENSE ? 3 : 3 + G.shift)) - 2) * inv_smax);
   }
-  if (!c.base) return 1.f;
-  return __ldg(base_tsdf(c.base) + voxel_index(px, py, pz));
+  return t;
+}
+
+// The march proper: from sample 0 to the first hit (returns true, position = the hit sample) or to the end of the ray.
+// Sample i sits at the position accumulated by i additions.  One round = one sample that is really looked up, followed
+// by the advance over it and over the `skip` samples after it that provably read +1 (they can neither start nor
+// complete a hit, voxel_tsdf.cu:260, and leave tsdf_prev at +1, which it already is: a sample with skip > 0 is itself
+// unallocated).  tsdf_prev starts negative so that sample 0 only initialises it, like the reference's pre-loop Retrieve.
+template <bool CLAMP, bool DENSE, class V>
+__device__ __forceinline__ bool march(const V& vol, const Grid& G, f32x2& pxy, float& pz, f32x2 sxy, float sz, float inv_smax, unsigned leaving,
+                                      int max_step) {
+  float tsdf_prev = -1.f;
+  int i = 0;
+  for (;;) {
+    int skip;
+    const float tsdf_curr = march_sample<CLAMP, DENSE>(vol, G, f3(lo2(pxy), hi2(pxy), pz), inv_smax, leaving, skip);
+    // ray hit front surface (voxel_tsdf.cu:260)
+    if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) return true;
+    tsdf_prev = tsdf_curr;
+    if (skip == kEscaped) return false;         // a miss, whose position nobody reads
+    const int k = min(skip, max_step - 1 - i);  // samples beyond max_step - 1 do not exist
+    pxy = add2(pxy, sxy); pz += sz;             // the step over the sample just taken
+    if (k > 0) {                                // ... and over the skipped ones: exactly the additions the reference performs
+      if (k & 1) { pxy = add2(pxy, sxy); pz += sz; }
+      if (k & 2) { pxy = add2(pxy, sxy); pz += sz; pxy = add2(pxy, sxy); pz += sz; }
+      if (k & 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { pxy = add2(pxy, sxy); pz += sz; }
+      }
+      for (int j = k >> 3; j > 0; --j) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { pxy = add2(pxy, sxy); pz += sz; }
+      }
+    }
+    i += k + 1;
+    if (i >= max_step) return false;
+  }
 }
 
 __device__ __forceinline__ unsigned char f2u8(float f) { return (unsigned char)min(255, max(0, __float2int_rz(f))); }
@@ -275,7 +323,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   const int idx = y * P.w + x;
   Grid G;
   G.ox = M.hdr[0]; G.oy = M.hdr[1]; G.oz = M.hdr[2]; G.nx = M.hdr[3]; G.ny = M.hdr[4]; G.nz = M.hdr[5]; G.shift = M.hdr[6];
-  G.dist = M.dist; G.index = M.index;
+  G.cells = M.cells;
 
   // voxel_tsdf.cu:243-250
   const float3 pos_cam = kmul(P.Kinv, f3((float)x, (float)y, 1.f));
@@ -304,50 +352,21 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   const float inv_smax = 1.f / (smax * 1.001f + 1e-6f);
 
   BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.base = nullptr;
-  int skip;
   // sides of the block AABB this ray can only move away from (see cell_distance)
   const unsigned leaving = (ray_step_grid.x <= 0.f ? 1u : 0u) | (ray_step_grid.y <= 0.f ? 2u : 0u) | (ray_step_grid.z <= 0.f ? 4u : 0u) |
                            (ray_step_grid.x >= 0.f ? 8u : 0u) | (ray_step_grid.y >= 0.f ? 16u : 0u) | (ray_step_grid.z >= 0.f ? 32u : 0u);
-  float tsdf_prev = march_sample<CLAMP>(vol, G, cache, pos_grid, inv_smax, leaving, skip);
   // x and y of the position live in one register pair for the whole march and advance in one FADD2 per step
   // (bit-identical to two scalar adds); reading a half of the pair is free
   f32x2 pxy = pack2(pos_grid.x, pos_grid.y);
   const f32x2 sxy = pack2(ray_step_grid.x, ray_step_grid.y);
   float pz = pos_grid.z;
   const float sz = ray_step_grid.z;
-  pxy = add2(pxy, sxy); pz += sz;
-  int i = 1;
 
   uint32_t out_rgba = 0u, out_normal = 0u;  // r | g << 8 | b << 16 | a << 24; a miss is (0, 0, 0, 0) like the reference
   float out_depth = CUDART_INF_F;
 
-  bool hit = false;
-  for (;;) {
-    if (skip > 0) {  // the next `skip` samples read +1: advance the position exactly as the reference does
-      if (skip == kEscaped) break;  // ... all of them: a miss, whose position nobody reads
-      const int k = min(skip, max_step - i);
-      if (k > 0) {
-        if (k & 1) { pxy = add2(pxy, sxy); pz += sz; }
-        if (k & 2) { pxy = add2(pxy, sxy); pz += sz; pxy = add2(pxy, sxy); pz += sz; }
-        if (k & 4) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { pxy = add2(pxy, sxy); pz += sz; }
-        }
-        for (int j = k >> 3; j > 0; --j) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { pxy = add2(pxy, sxy); pz += sz; }
-        }
-        i += k;
-      }
-    }
-    if (i >= max_step) break;
-    const float tsdf_curr = march_sample<CLAMP>(vol, G, cache, f3(lo2(pxy), hi2(pxy), pz), inv_smax, leaving, skip);
-    // ray hit front surface (voxel_tsdf.cu:260)
-    if (tsdf_prev > 0 && tsdf_curr <= 0 && tsdf_prev - tsdf_curr <= 1.5f) { hit = true; break; }
-    tsdf_prev = tsdf_curr;
-    pxy = add2(pxy, sxy); pz += sz;
-    ++i;
-  }
+  const bool hit = G.shift == 0 ? march<CLAMP, true>(vol, G, pxy, pz, sxy, sz, inv_smax, leaving, max_step)
+                                : march<CLAMP, false>(vol, G, pxy, pz, sxy, sz, inv_smax, leaving, max_step);
   pos_grid = f3(lo2(pxy), hi2(pxy), pz);
 
   // The refinement runs after the march loop so that the lanes of a warp execute it together (once per
@@ -439,8 +458,7 @@ static bool view_needs_clamp(const FrameParams& P, float step_size) {
 void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, const SkipMap& M, uchar4* rgba,
                     uchar4* normal, float* hit_depth, unsigned long long* packed_keys, cudaStream_t st) {
   dim3 grid((P.w + 31) / 32, (P.h + 7) / 8);
-  SkipMap R = M;  // launch_build_skip_map leaves the final distances in `scratch`
-  R.dist = M.scratch; R.scratch = M.dist;
+  const SkipMap& R = M;
   Volume<false> vol; vol.S = S;
   if (view_needs_clamp(P, step_size)) raycast_kernel<false, true><<<grid, 256, 0, st>>>(vol, P, step_size, R, 0, P.h, rgba, normal, hit_depth, packed_keys);
   else raycast_kernel<false, false><<<grid, 256, 0, st>>>(vol, P, step_size, R, 0, P.h, rgba, normal, hit_depth, packed_keys);
@@ -454,8 +472,7 @@ void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift
                            int n_out, void* const* out_rgba, void* const* out_normal, void* const* out_depth, cudaStream_t st) {
   if (rows <= 0) return;
   dim3 grid((P.w + 31) / 32, (rows + 7) / 8);
-  SkipMap R = M;
-  R.dist = M.scratch; R.scratch = M.dist;
+  const SkipMap& R = M;
   Volume<true> vol; vol.shards = shards; vol.n_shards = n_shards; vol.shard_shift = shard_shift;
   vol.n_out = n_out;
   for (int r = 0; r < kMaxPeers; ++r) {
