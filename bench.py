@@ -176,7 +176,7 @@ def oracle_threads():
 
 def oracle_step(o, cfg, st, i):
     o.integrate(st["rgb"][i], st["depth"][i], st["ht"][i], st["lt"][i], cfg.max_depth, st["K"], st["q"][i], st["t"][i])
-    o.raycast(cfg.max_depth, cfg.width, cfg.height, st["K"], st["q"][i], st["t"][i])
+    return o.raycast(cfg.max_depth, cfg.width, cfg.height, st["K"], st["q"][i], st["t"][i])[3]
 
 
 def cpu_sample(cfg, st, budget_s, max_frames):
@@ -184,12 +184,20 @@ def cpu_sample(cfg, st, budget_s, max_frames):
     from oracle.oracle import Oracle
     o = Oracle(cfg.voxel_size, cfg.truncation)
     n, t0 = 0, time.perf_counter()
+    samples = switches = hits = 0
     while n < max_frames and (n < 2 or time.perf_counter() - t0 < budget_s):
-        oracle_step(o, cfg, st, n)
+        c = oracle_step(o, cfg, st, n)
+        samples, switches, hits = samples + c["samples"], switches + c["block_switches"], hits + c["hits"]
         n += 1
     dt = time.perf_counter() - t0
     o.close()
-    return n / dt, n, dt
+    # B_ray = sum over rays (4 B per sample + 12 B per block switch) + 8 B per ray written (+ 4 B hit depth)
+    rays = cfg.width * cfg.height
+    ray_stats = {"frames_counted": n, "samples_per_ray": samples / (n * rays), "block_switches_per_ray": switches / (n * rays),
+                 "hit_fraction": hits / (n * rays), "algorithmic_bytes_per_view": (4 * samples + 12 * switches) / n + 12 * rays,
+                 "model": "the reference's march counted by the oracle (every sample looked up, 12-byte hash entry per block switch): "
+                          "4 B x samples + 12 B x block switches + 12 B per ray written (rgba, normal, hit depth)"}
+    return n / dt, n, dt, ray_stats
 
 
 def run_reference(args, cfg, rank, world):
@@ -746,7 +754,7 @@ def main():
         "gather": gather,
         "raycast": {"us_per_view": 1e3 * ph_ms.get("raycast", 0.0) / max(ph_n.get("raycast", 0), 1), "rays_per_view": npx,
                     "mrays_per_s_kernel_only": npx * ph_n.get("raycast", 0) / (ph_ms.get("raycast", 1e-9) * 1e-3) / 1e6,
-                    "note": "skip-map build + march; issue/latency bound (ncu: DRAM < 6 % of peak), not an HBM-roofline kernel"},
+                    "note": "skip-map maintenance (4 launches, skipped when the block set did not change) + march; instruction-issue bound (ncu: 86 % issue-active, DRAM < 6 % of peak), not an HBM-roofline kernel"},
         "e2e": e2e,
         "e2e_u16": e2e_u16,
         "e2e_sync": e2e_sync,
@@ -757,7 +765,11 @@ def main():
     }
     line["configs"] = extra
     if not args.no_cpu_baseline and world == 1:
-        v, n, dt = cpu_sample(cfg, streams[0], args.cpu_seconds, n_frames)
+        v, n, dt, ray_stats = cpu_sample(cfg, streams[0], args.cpu_seconds, n_frames)
+        rc_us = line["raycast"]["us_per_view"]
+        line["raycast"].update(ray_stats)
+        line["raycast"]["algorithmic_gbs"] = ray_stats["algorithmic_bytes_per_view"] / (rc_us * 1e-6) / 1e9 if rc_us else None
+        line["raycast"]["cache_hit_rates_ncu"] = tj.get("raycast_kernel_hit_rates")
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": oracle_threads(), "kind": "port",
                                 "sample": f"first {n} frames of stream 0 (Integrate + RayCast each), {dt:.1f} s; oracle/tsdf_oracle.c -O2, "
                                           "OpenMP over visible blocks and image rows, allocation pass scalar"}

@@ -59,6 +59,28 @@ class TSDFGrid {
                          img_depth.rows, max_depth, K, q, t));
   }
 
+  // The sensor's own formats: CV_16UC1 depth (metres = value / depthmap_factor) and CV_16UC1 probabilities (value / 65535)
+  // -- what the reference holds before `convertTo(CV_32FC1, 1. / scale)` (examples/tsdf/offline.cc:72-83).  The conversion
+  // runs on the GPU with convertTo's arithmetic; 9 bytes per pixel cross PCIe instead of 15.  ht / lt may be empty Mats
+  // (TSDFSystem's default of ones, modules/tsdf_module.cc:28-33).
+  template <class Mat, class Intrinsics, class Pose>
+  void IntegrateU16(const Mat& img_rgb, const Mat& depth_u16, const Mat& ht_u16, const Mat& lt_u16, float depthmap_factor, float max_depth,
+                    const Intrinsics& intrinsics, const Pose& cam_T_world, int flags = 0) {
+    constexpr int kCV_16UC1 = 2;
+    if (img_rgb.type() != kCV_8UC3 || depth_u16.type() != kCV_16UC1 || img_rgb.cols != depth_u16.cols || img_rgb.rows != depth_u16.rows)
+      throw Error(TSDF_E_INVALID, "IntegrateU16: rgb must be CV_8UC3, depth CV_16UC1, same size");
+    const bool probs = ht_u16.total() != 0 || lt_u16.total() != 0;
+    if (probs && (ht_u16.type() != kCV_16UC1 || lt_u16.type() != kCV_16UC1 || ht_u16.total() != depth_u16.total() || lt_u16.total() != depth_u16.total()))
+      throw Error(TSDF_E_INVALID, "IntegrateU16: ht / lt must be CV_16UC1 of the size of depth, or both empty");
+    const float K[4] = {intrinsics.fx, intrinsics.fy, intrinsics.cx, intrinsics.cy};
+    float q[4], t[3];
+    unpack(cam_T_world, q, t);
+    check(tsdf_integrate_u16(h_, reinterpret_cast<const uint8_t*>(img_rgb.data), reinterpret_cast<const uint16_t*>(depth_u16.data),
+                             probs ? reinterpret_cast<const uint16_t*>(ht_u16.data) : nullptr,
+                             probs ? reinterpret_cast<const uint16_t*>(lt_u16.data) : nullptr, depth_u16.cols, depth_u16.rows, depthmap_factor,
+                             max_depth, K, q, t, flags));
+  }
+
   // Images are sinks with LoadCuda(device pointer); nullptr skips that output like the reference.
   template <class CamParams, class Pose, class ImageA = std::nullptr_t, class ImageB = std::nullptr_t>
   void RayCast(float max_depth, const CamParams& virtual_cam, const Pose& cam_T_world, ImageA* tsdf_rgba = nullptr,

@@ -17,7 +17,14 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct",
            "l1tex__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
-           "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_lsu.sum"]
+           "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_lsu.sum",
+           "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+           "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
 
 
 def launches(tag):
@@ -66,6 +73,12 @@ def full(tag):
     tj = {"source": f"profiles/{tag}_full.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"}
     for name, v in acc.items():
         tj[name] = {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v)}
+    # cache hit rates of the ray caster's look-ups (BASELINE north_star asks for the L2 hit rate of the probes)
+    l1, l2 = h.index("l1tex__t_sector_hit_rate.pct"), h.index("lts__t_sector_hit_rate.pct")
+    rc = [r for r in rows if "raycast_kernel" in r[ki]]
+    if rc:
+        tj["raycast_kernel_hit_rates"] = {"l1tex_sector_hit_pct": sum(float(r[l1]) for r in rc) / len(rc),
+                                          "l2_sector_hit_pct": sum(float(r[l2]) for r in rc) / len(rc), "launches": len(rc)}
     json.dump(tj, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     print("\n".join(out[:20]))
 

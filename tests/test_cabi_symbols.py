@@ -70,3 +70,15 @@ def test_multi_gpu_data_plane_header_and_binding_agree(tsdf_lib):
     needed = subprocess.run(["readelf", "-d", mgpu.LIB_PATH], capture_output=True, text=True).stdout
     assert "libnccl.so" in needed and "libtsdf_b200.so" in needed and "torch" not in needed
     assert L.tsdf_mgpu_destroy(None) == 0
+
+
+def test_cpp_host_headers_compile(tmp_path):
+    """The header-only C++17 mirrors (TSDFGrid incl. IntegrateU16, ShardedVolume over the NCCL data plane) compile with
+    nothing but the C ABI headers -- no Eigen, OpenCV, CUDA or torch headers."""
+    import subprocess
+    src = tmp_path / "hdr_check.cc"
+    src.write_text('#include "tsdf_b200/sharded_volume.hpp"\n#include "tsdf_b200/voxel_tsdf.hpp"\n#include "tsdf_b200/tsdf_system.hpp"\n'
+                   'int main() { return sizeof(tsdf_b200::ShardedVolume) + sizeof(tsdf_b200::TSDFGrid) > 0 ? 0 : 1; }\n')
+    res = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "o.o")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr

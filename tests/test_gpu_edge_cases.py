@@ -58,6 +58,50 @@ def test_raycast_on_hand_built_sparse_volumes(tg, blocks):
     g.close()
 
 
+def test_raycast_while_the_map_layout_changes(tg):
+    """The skip map is rebuilt without a fill pass: its two byte planes swap roles and the rebuild restores the plane it
+    will mark into next.  A volume that GROWS between views changes the layout every time -- from 3.4 M cells at one
+    block per cell, to 0.8 M coarser cells (the cell count shrinks), back up to 3.4 M coarser cells, then to the
+    largest shift -- and a view in between deletes blocks again.  Every view must equal the oracle."""
+    near = [[0, 0, 10], [1, 0, 10], [0, 1, 10], [1, 1, 10], [-1, -1, 10]]
+    g, o = slab_volume(tg, near + [[149, 149, 159]])                       # AABB 151 x 151 x 150 cells, shift 0
+    K = (300.0, 300.0, 159.5, 119.5)
+    cam = tg.CameraParams(K, 240, 320)
+    ident = np.array([0, 0, 0, 1], np.float32)
+    views = [(ident, np.zeros(3, np.float32), 4.0), (ident, np.array([-0.08, -0.05, 0.3], np.float32), 10.0)]
+    rng = np.random.RandomState(11)
+
+    def add(blocks):
+        g.allocate_blocks(blocks)
+        for b in blocks:
+            o.allocate_block(*b)
+            pts = np.array([[b[0] * 8 + x, b[1] * 8 + y, b[2] * 8 + z] for z in range(8) for y in range(8) for x in range(8)], np.int32)
+            tsdf = np.clip((3.5 - (pts[:, 2] - b[2] * 8)) / 6.0, -1, 1).astype(np.float32)
+            rgbw = np.concatenate([rng.randint(0, 255, (512, 3)), np.full((512, 1), 7)], 1).astype(np.uint8)
+            g.assign(pts, tsdf=tsdf, rgbw=rgbw)
+            o.set_voxels(pts, tsdf=tsdf, rgbw=rgbw)
+
+    def check(label):
+        hits = 0
+        for q, t, md in views:
+            hits += compare.compare_raycast(g.RayCast(md, cam, (q, t)), o.raycast(md, 320, 240, np.array(K, np.float32), q, t)[:3], label)["hits"]
+        assert hits > 500, label
+
+    check("shift 0, 3.4 M cells")
+    add([[300, 100, 100]])                                                   # 302 x 151 x 150 blocks: shift 1, 0.86 M cells
+    check("shift 1, fewer cells than before")
+    add([[300, 300, 309], [2, 2, 10]])                                      # 302 x 302 x 300 blocks at shift 1: 3.4 M cells
+    check("shift 1, as many cells as the first layout")
+    g.delete_blocks([[1, 1, 10]])
+    o.delete_block(1, 1, 10)
+    check("after deleting a block (same layout)")
+    add([[-3000, 5, 7], [0, 1, 11]])                                        # a much larger shift
+    check("large shift")
+    attempts, rebuilds = g.skip_map_stats()
+    assert rebuilds == 5 and attempts == 5  # one rebuild per change, none for the second view of a pair
+    g.close()
+
+
 def test_raycast_at_the_edge_of_the_short_range(tg):
     """A camera 655 m from the origin at 2 cm voxels: sample coordinates pass -32768 and the reference's float -> short
     cast saturates (utils/tsdf/voxel_mem.cuh via .cast<short>()).  The engine picks its clamping ray-cast variant for
