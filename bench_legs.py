@@ -67,6 +67,26 @@ class DeviceTimer:
         return self.a.elapsed_time(self.b)
 
 
+def nvlink_bytes(local_rank):
+    """(tx, rx) bytes this GPU has moved over NVLink so far (NVML throughput counters, KiB granularity), or None."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        out = []
+        for fid in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX):
+            v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, pynvml.NVML_NVLINK_MAX_LINKS)])[0]  # scope = all links
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal) * 1024)
+        return tuple(out)
+    except Exception:
+        return None
+
+
 def max_over_ranks(torch, dist, world, dev, v):
     if world == 1:
         return v
@@ -234,7 +254,9 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
     seq(0, n_tour, 0)          # the tour that builds the volume
     seq(n_tour, W, 1)          # warm-up with views
+    nv0 = nvlink_bytes(local_rank)
     ms_rc, cms, cn, tot, n_act = timed(n_tour + W, K, 1)
+    nv1 = nvlink_bytes(local_rank)
     # parity, outside every timed region: the last exact view against a single-GPU engine fed the same history
     img = np.empty((H, Wd, 4), np.uint8), np.empty((H, Wd, 4), np.uint8), np.empty((H, Wd), np.float32)
     mgpu.check(vol.L.tsdf_mgpu_fetch_images(vol.h, img[0].ctypes.data, img[1].ctypes.data, img[2].ctypes.data))
@@ -256,6 +278,11 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
             "note": "CUDA events around each step on its stream (a barrier's time includes waiting for the slowest rank); the frame broadcast "
                     "(grouped ncclBroadcast) runs on its own stream and overlaps the previous frame's kernels; on the engine stream there is no NCCL "
                     "kernel: the image rows travel as posted NVLink stores issued by the march kernel itself"}
+    if nv0 and nv1:  # what rank 0's GPU really moved over NVLink per frame (NVML link counters around the timed frames)
+        coll["nvlink_bytes_per_frame_rank0"] = {"tx": (nv1[0] - nv0[0]) / K, "rx": (nv1[1] - nv0[1]) / K,
+                                                "source": "NVML NVLINK_THROUGHPUT_DATA_TX / RX, all links of rank 0's GPU; rank 0 is the broadcast root, so tx "
+                                                          "carries the frame planes once per ring hop plus its image rows to 7 peers, rx the peers' rows and the voxels "
+                                                          "its march read from other shards"}
     on_path = {"frame_broadcast_us": coll["frame_broadcast_us"] or 0.0,
                "peer_barriers_us": (coll["peer_barrier_before_march_us"] or 0.0) + (coll["peer_barrier_after_march_us"] or 0.0)}
     res3.update({"active_voxels": 512 * n_act, "active_blocks": n_act, "sharded_parity": parity,

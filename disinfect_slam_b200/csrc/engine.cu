@@ -750,11 +750,11 @@ int tsdf_peer_attach_local(tsdf_handle e, int world, const tsdf_handle* shards) 
 }
 
 static int raycast_shared_impl(tsdf_engine* e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
-                               int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth, int n_out, void* const* out_rgba,
-                               void* const* out_normal, void* const* out_depth) {
+                               int row0, int rows, int tile_stride, void* d_rgba, void* d_normal, void* d_hit_depth, int n_out,
+                               void* const* out_rgba, void* const* out_normal, void* const* out_depth) {
   if (!e || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
   if (e->n_peers < 1) return fail(TSDF_E_INVALID, "no peers attached (tsdf_ipc_attach / tsdf_peer_attach_local)");
-  if (w <= 0 || h <= 0 || row0 < 0 || rows < 0) return fail(TSDF_E_INVALID, "bad image size / row range");
+  if (w <= 0 || h <= 0 || row0 < 0 || rows < 0 || tile_stride < 1) return fail(TSDF_E_INVALID, "bad image size / row range");
   if (n_out < 0 || n_out > kMaxPeers) return fail(TSDF_E_INVALID, "at most %d destinations", kMaxPeers);
   CU(cudaSetDevice(e->device));
   const FrameParams P = make_params(e, w, h, max_depth, K, q, t);
@@ -763,7 +763,7 @@ static int raycast_shared_impl(tsdf_engine* e, float max_depth, int w, int h, co
   // the kernels return at once when no shard's block set changed since the last build (device-side serials)
   launch_build_skip_map(e->d_peers, e->n_peers, e->skip, ++e->skip_gen, true, e->num_sms, e->stream);
   e->skip_epoch = 0;  // a local RayCast must look again: the map may describe more than this engine
-  launch_raycast_shared(e->d_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0),
+  launch_raycast_shared(e->d_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0), tile_stride,
                         (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, n_out, out_rgba, out_normal, out_depth, e->stream);
   phase_end(e, PH_RAYCAST, e->stream);
   CU(cudaGetLastError());
@@ -771,12 +771,16 @@ static int raycast_shared_impl(tsdf_engine* e, float max_depth, int w, int h, co
 }
 int tsdf_raycast_shared(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
                         int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth) {
-  return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, d_rgba, d_normal, d_hit_depth, 0, nullptr, nullptr, nullptr);
+  return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, 1, d_rgba, d_normal, d_hit_depth, 0, nullptr, nullptr, nullptr);
 }
 int tsdf_raycast_shared_scatter(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
-                                int row0, int rows, int n_dest, void* const* d_rgba, void* const* d_normal, void* const* d_hit_depth) {
+                                int tile_first, int tile_stride, int n_dest, void* const* d_rgba, void* const* d_normal,
+                                void* const* d_hit_depth) {
   if (n_dest < 1) return fail(TSDF_E_INVALID, "need at least one destination");
-  return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, nullptr, nullptr, nullptr, n_dest, d_rgba, d_normal, d_hit_depth);
+  if (tile_first < 0 || tile_stride < 1) return fail(TSDF_E_INVALID, "bad tile selection");
+  if (tile_first * 8 >= h) return TSDF_OK;  // more ranks than tiles
+  return raycast_shared_impl(e, max_depth, w, h, K, q, t, tile_first * 8, h - tile_first * 8, tile_stride, nullptr, nullptr, nullptr, n_dest, d_rgba,
+                             d_normal, d_hit_depth);
 }
 
 // Large results (GatherValid / GatherVoxels records, meshes) to host memory at PCIe speed.

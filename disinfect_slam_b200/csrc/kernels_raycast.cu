@@ -167,6 +167,9 @@ template <> struct Volume<true> {
   // (peer-mapped pointers, posted stores over NVLink issued as the rays finish) instead of into one local image that an
   // all-gather would have to distribute afterwards.
   int n_out; uchar4* out_rgba[kMaxPeers]; uchar4* out_normal[kMaxPeers]; float* out_depth[kMaxPeers];
+  // which 8-row tiles this launch renders: tile_first, tile_first + tile_stride, ...  (stride 1 = a contiguous band;
+  // stride = number of ranks interleaves the tiles of a view over the ranks, so that all of them finish together)
+  int tile_stride;
   __device__ __forceinline__ const unsigned char* at(int entry) const {  // owner shard in the top bits: no table probe over NVLink
     return shards[entry >> kIndexShardShift].voxels + (size_t)(entry & ((1 << kIndexShardShift) - 1)) * kBlockBytes;
   }
@@ -310,6 +313,9 @@ __device__ __forceinline__ bool march(const V& vol, const Grid& G, f32x2& pxy, f
 __device__ __forceinline__ unsigned char f2u8(float f) { return (unsigned char)min(255, max(0, __float2int_rz(f))); }
 __device__ __forceinline__ float3 add3(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 
+__device__ __forceinline__ int tile_stride_of(const Volume<false>&) { return 1; }
+__device__ __forceinline__ int tile_stride_of(const Volume<true>& v) { return v.tile_stride; }
+
 template <bool SHARED, bool CLAMP>
 __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameParams P, float step_size, SkipMap M, int row0,
                                                       int rows, uchar4* __restrict__ img_rgba, uchar4* __restrict__ img_normal,
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   // image rows [row0, row0 + rows)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-  const int y = row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+  const int y = row0 + (SHARED ? (int)blockIdx.y * tile_stride_of(vol) : (int)blockIdx.y) * 8 + (warp >> 2) * 4 + (lane >> 3);
   if (x >= P.w || y >= P.h || y >= row0 + rows) return;
   const int idx = y * P.w + x;
   Grid G;
@@ -468,13 +474,17 @@ void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size,
 // mapped in `shards` (device array): bit-identical to the single-volume render, voxels of foreign blocks are read
 // from their owner over NVLink.
 void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
-                           const SkipMap& M, int row0, int rows, uchar4* rgba, uchar4* normal, float* hit_depth,
+                           const SkipMap& M, int row0, int rows, int tile_stride, uchar4* rgba, uchar4* normal, float* hit_depth,
                            int n_out, void* const* out_rgba, void* const* out_normal, void* const* out_depth, cudaStream_t st) {
   if (rows <= 0) return;
-  dim3 grid((P.w + 31) / 32, (rows + 7) / 8);
+  // tile_stride > 1: `rows` bounds the rows of the image this launch may touch ([row0, row0 + rows)), of which it
+  // renders every tile_stride-th 8-row tile starting at row0
+  const int n_tiles = ((rows + 7) / 8 + tile_stride - 1) / tile_stride;
+  dim3 grid((P.w + 31) / 32, n_tiles);
   const SkipMap& R = M;
   Volume<true> vol; vol.shards = shards; vol.n_shards = n_shards; vol.shard_shift = shard_shift;
   vol.n_out = n_out;
+  vol.tile_stride = tile_stride;
   for (int r = 0; r < kMaxPeers; ++r) {
     vol.out_rgba[r] = r < n_out && out_rgba ? (uchar4*)out_rgba[r] : nullptr;
     vol.out_normal[r] = r < n_out && out_normal ? (uchar4*)out_normal[r] : nullptr;

@@ -369,7 +369,8 @@ int tsdf_mgpu_raycast(tsdf_mgpu_handle m, float max_depth, int w, int h, const f
       Timed tm(m, T_RAYCAST, m->es);
       void* o[3][kMaxRanks];
       for (int i = 0; i < 3; ++i) for (int r = 0; r < m->world; ++r) o[i][r] = m->xpeer[r] + (size_t)i * m->img_stride;
-      if (row0 < h) TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, row0, rows, m->world, o[0], o[1], o[2]));
+      // 8-row tiles dealt out round-robin: every rank renders the same mix of rows
+      TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, m->rank, m->world, m->world, o[0], o[1], o[2]));
     }
     { Timed tm(m, T_ALLGATHER, m->es); int rc2 = peer_barrier(m); if (rc2) return rc2; }
   } else {

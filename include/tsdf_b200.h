@@ -197,9 +197,12 @@ int tsdf_raycast_shared(tsdf_handle h, float max_depth, int width, int height, c
 /* Same march, with the exchange of the results fused into the kernel: every finished ray is stored into the HxW images
  * of n_dest destinations (device pointers, typically the image buffers of every rank mapped as peer memory; entries or
  * whole arrays may be NULL) -- posted stores over NVLink while the march runs, instead of a local image plus an
- * all-gather afterwards.  The caller orders the destinations' readers with its own barrier. */
+ * all-gather afterwards.  The launch renders the 8-row tiles tile_first, tile_first + tile_stride, ... of the view:
+ * with tile_first = rank and tile_stride = number of ranks the tiles of a view are dealt out round-robin, so every rank
+ * gets the same mix of cheap and expensive rows and all of them finish together.  The caller orders the destinations'
+ * readers with its own barrier. */
 int tsdf_raycast_shared_scatter(tsdf_handle h, float max_depth, int width, int height, const float K[4],
-                                const float q_xyzw[4], const float t_xyz[3], int row0, int rows, int n_dest,
+                                const float q_xyzw[4], const float t_xyz[3], int tile_first, int tile_stride, int n_dest,
                                 void* const* d_rgba, void* const* d_normal, void* const* d_hit_depth);
 
 /* TSDFGrid::GatherValid()                               utils/tsdf/voxel_tsdf.cu:399-425
