@@ -216,8 +216,9 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                               [planes(s) for s in range(n_hist + 2 * K)] if rank == 0 else None)
     import os
 
-    def make_volume(exchange):
+    def make_volume(exchange, mirror=True):
         os.environ["TSDF_MGPU_EXCHANGE"] = exchange  # read by tsdf_mgpu_create
+        os.environ["TSDF_MGPU_MIRROR"] = "1" if mirror else "0"
         return mgpu.ShardedVolume(VOXEL3, TRUNC3, rank, world, fresh_id(), device=local_rank, pool_blocks=pool_rank,
                                   table_slots=max(1 << 16, 1 << int(np.ceil(np.log2(4 * pool_rank)))), max_image_pixels=big, shard_shift=2)
 
@@ -249,7 +250,19 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     nccl_variant = {"frames_per_s": K / (ms_n * 1e-3), "us_per_frame": 1e3 * ms_n / K, "barrier_allreduce_us": per(cms_n, cn_n, "barrier"),
                     "image_allgather_us": per(cms_n, cn_n, "allgather"), "raycast_shared_kernels_us": per(cms_n, cn_n, "raycast_shared"),
                     "exchange": "TSDF_MGPU_EXCHANGE=nccl: 4-byte ncclAllReduce, march into a local image, grouped in-place ncclAllGather of 12 B/px"}
-    # the product path: exchange fused into the march kernel, peer barriers instead of collectives
+    # fused exchange, but every TSDF sample of a foreign block loaded over NVLink (no mirrors): memory per rank = its shard only
+    vol = make_volume("fused", mirror=False)
+    tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
+    seq(0, n_tour, 0)
+    seq(n_tour, W, 1)
+    ms_m, cms_m, cn_m, _, _ = timed(n_tour + W, K, 1)
+    vol.close()
+    barrier(torch, dist, world)
+    nomirror_variant = {"frames_per_s": K / (ms_m * 1e-3), "us_per_frame": 1e3 * ms_m / K, "peer_barrier_before_march_us": per(cms_m, cn_m, "barrier"),
+                        "march_with_fused_scatter_us": per(cms_m, cn_m, "raycast_shared"), "peer_barrier_after_march_us": per(cms_m, cn_m, "allgather"),
+                        "exchange": "TSDF_MGPU_MIRROR=0: fused exchange, foreign voxels loaded from their owner over NVLink sample by sample"}
+    # the product path: exchange fused into the march kernel, peer barriers instead of collectives, TSDF mirrors kept current
+    # by the integrate kernels
     vol = make_volume("fused")
     tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
     seq(0, n_tour, 0)          # the tour that builds the volume
@@ -292,9 +305,11 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                                     "broadcast_us": per(cms_i, cn_i, "broadcast")},
                  "integrate_raycast_min_composite": {"frames_per_s": K / (ms_cmp * 1e-3), "us_per_frame": 1e3 * ms_cmp / K},
                  "collectives": coll, "limiting_collective": max(on_path, key=on_path.get), "nccl_exchange_variant": nccl_variant,
+                 "no_mirror_variant": nomirror_variant,
                  "path": "libtsdf_b200_mgpu.so: tsdf_mgpu_run_sequence (C++ loop, NCCL linked directly): grouped ncclBroadcast of the planes from rank 0's HBM, "
-                         "owner-filtered allocate + integrate, peer barrier kernel, tsdf_raycast_shared_scatter (each rank marches 1/N of the rows over peer "
-                         "memory and stores them into every rank's images), peer barrier kernel; CUDA events on the engine stream, max over ranks; voxel "
+                         "owner-filtered allocate + integrate (every updated TSDF value also stored into all ranks' TSDF mirrors), peer barrier kernel, "
+                         "tsdf_raycast_shared_scatter (each rank marches 1/N of the 8-row tiles, TSDF samples from its local mirror, hit colours from the "
+                         "owner over NVLink, and stores the finished rays into every rank's images), peer barrier kernel; CUDA events on the engine stream, max over ranks; voxel "
                          "updates all-reduced"})
     # config 4 on the sharded volume: exact (rows split) and min-composited (whole views per rank)
     for md in (4.0, 10.0):

@@ -60,7 +60,8 @@ SYMBOLS = {
     "tsdf_ipc_attach": (_i32, [_vp, _i32, _vp]),
     "tsdf_peer_attach_local": (_i32, [_vp, _i32, _vp]),
     "tsdf_raycast_shared": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "tsdf_raycast_shared_scatter": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "tsdf_mirror_attach": (_i32, [_vp, _i32, _vp, _i32]),
+    "tsdf_raycast_shared_scatter": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "tsdf_gather_valid": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_in_bound": (_i32, [_vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_fetch": (_i32, [_vp, _vp, _i64]),

@@ -63,6 +63,8 @@ struct tsdf_engine {
   SkipMap skip{};                    // RayCast empty-space skip map, rebuilt when the block set changed
   PeerView* d_self = nullptr;        // device copy of this engine's own PeerView (1 entry)
   PeerView* d_peers = nullptr;       // device array [shard_count]: every shard of a volume sharded over GPUs
+  PeerView h_peers[kMaxPeers] = {};  // the same on the host (pool pointers travel as kernel parameters)
+  uint64_t shared_epoch = 0;         // volume_epoch at the last shared-map build attempt (see tsdf_raycast_shared_scatter)
   int n_peers = 0;
   void* ipc_opened[kMaxPeers][4] = {};  // pointers obtained from cudaIpcOpenMemHandle (closed at destroy)
   uint64_t volume_epoch = 1, skip_epoch = 0;  // host side: a mutating call was enqueued since the map was last looked at
@@ -728,6 +730,7 @@ int tsdf_ipc_attach(tsdf_handle e, int world, const void* blobs) {
     views[r].voxels = (const unsigned char*)p[2]; views[r].ctr = (const int*)p[3];
   }
   CU(cudaMemcpy(e->d_peers, views, sizeof(PeerView) * world, cudaMemcpyHostToDevice));
+  memcpy(e->h_peers, views, sizeof(PeerView) * world);
   e->n_peers = world;
   return TSDF_OK;
 }
@@ -745,13 +748,14 @@ int tsdf_peer_attach_local(tsdf_handle e, int world, const tsdf_handle* shards) 
     views[r] = self_view(o);
   }
   CU(cudaMemcpy(e->d_peers, views, sizeof(PeerView) * world, cudaMemcpyHostToDevice));
+  memcpy(e->h_peers, views, sizeof(PeerView) * world);
   e->n_peers = world;
   return TSDF_OK;
 }
 
 static int raycast_shared_impl(tsdf_engine* e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
-                               int row0, int rows, int tile_stride, void* d_rgba, void* d_normal, void* d_hit_depth, int n_out,
-                               void* const* out_rgba, void* const* out_normal, void* const* out_depth) {
+                               int row0, int rows, int tile_stride, bool peers_unchanged, void* d_rgba, void* d_normal, void* d_hit_depth,
+                               int n_out, void* const* out_rgba, void* const* out_normal, void* const* out_depth) {
   if (!e || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
   if (e->n_peers < 1) return fail(TSDF_E_INVALID, "no peers attached (tsdf_ipc_attach / tsdf_peer_attach_local)");
   if (w <= 0 || h <= 0 || row0 < 0 || rows < 0 || tile_stride < 1) return fail(TSDF_E_INVALID, "bad image size / row range");
@@ -761,26 +765,46 @@ static int raycast_shared_impl(tsdf_engine* e, float max_depth, int w, int h, co
   phase_begin(e, PH_RAYCAST, e->stream);
   // union of every shard's blocks.  Other shards change without this host knowing, so the attempt is always launched;
   // the kernels return at once when no shard's block set changed since the last build (device-side serials)
-  launch_build_skip_map(e->d_peers, e->n_peers, e->skip, ++e->skip_gen, true, e->num_sms, e->stream);
+  // ... unless the caller vouches that no shard has integrated since this engine's last shared view (the data plane knows:
+  // all ranks make the same calls) and this engine has not either: then even the four empty launches are saved
+  if (!(peers_unchanged && e->shared_epoch == e->volume_epoch && e->skip_epoch == 0 && e->skip_gen > 0))
+    launch_build_skip_map(e->d_peers, e->n_peers, e->skip, ++e->skip_gen, true, e->num_sms, e->stream);
+  e->shared_epoch = e->volume_epoch;
   e->skip_epoch = 0;  // a local RayCast must look again: the map may describe more than this engine
-  launch_raycast_shared(e->d_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0), tile_stride,
-                        (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, n_out, out_rgba, out_normal, out_depth, e->stream);
+  launch_raycast_shared(e->d_peers, e->h_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0), tile_stride,
+                        e->S.n_mirror ? e->S.mirror[e->S.shard_rank] : nullptr, e->S.mirror_stride, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, n_out, out_rgba, out_normal, out_depth, e->stream);
   phase_end(e, PH_RAYCAST, e->stream);
   CU(cudaGetLastError());
   return TSDF_OK;
 }
+int tsdf_mirror_attach(tsdf_handle e, int world, void* const* mirrors, int stride_blocks) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  if (rc) return rc;
+  if (world == 0 || !mirrors) { e->S.n_mirror = 0; return TSDF_OK; }
+  if (world != e->S.shard_count || world > kMaxPeers) return fail(TSDF_E_INVALID, "mirror count %d must equal shard_count %d", world, e->S.shard_count);
+  if (stride_blocks < e->S.pool_blocks) return fail(TSDF_E_INVALID, "mirror stride %d smaller than the pool (%d blocks)", stride_blocks, e->S.pool_blocks);
+  for (int r = 0; r < world; ++r) {
+    if (!mirrors[r]) return fail(TSDF_E_INVALID, "null mirror pointer for rank %d", r);
+    e->S.mirror[r] = (float*)mirrors[r];
+  }
+  e->S.n_mirror = world; e->S.mirror_stride = stride_blocks;
+  return TSDF_OK;
+}
+
 int tsdf_raycast_shared(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
                         int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth) {
-  return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, 1, d_rgba, d_normal, d_hit_depth, 0, nullptr, nullptr, nullptr);
+  return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, 1, false, d_rgba, d_normal, d_hit_depth, 0, nullptr, nullptr, nullptr);
 }
 int tsdf_raycast_shared_scatter(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
-                                int tile_first, int tile_stride, int n_dest, void* const* d_rgba, void* const* d_normal,
-                                void* const* d_hit_depth) {
+                                int tile_first, int tile_stride, int peers_unchanged, int n_dest, void* const* d_rgba,
+                                void* const* d_normal, void* const* d_hit_depth) {
   if (n_dest < 1) return fail(TSDF_E_INVALID, "need at least one destination");
   if (tile_first < 0 || tile_stride < 1) return fail(TSDF_E_INVALID, "bad tile selection");
   if (tile_first * 8 >= h) return TSDF_OK;  // more ranks than tiles
-  return raycast_shared_impl(e, max_depth, w, h, K, q, t, tile_first * 8, h - tile_first * 8, tile_stride, nullptr, nullptr, nullptr, n_dest, d_rgba,
-                             d_normal, d_hit_depth);
+  return raycast_shared_impl(e, max_depth, w, h, K, q, t, tile_first * 8, h - tile_first * 8, tile_stride, peers_unchanged != 0, nullptr, nullptr,
+                             nullptr, n_dest, d_rgba, d_normal, d_hit_depth);
 }
 
 // Large results (GatherValid / GatherVoxels records, meshes) to host memory at PCIe speed.

@@ -423,6 +423,10 @@ __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kerne
       item_min = fminf(item_min, fminf(fminf(fabsf(tsdf[0]), fabsf(tsdf[1])), fminf(fabsf(tsdf[2]), fabsf(tsdf[3]))));
       if ((upd & 15u) || is_new) {  // a block that turns out to be carved is released anyway: writing it is harmless
         st16(base_tsdf + slab * 128, make_float4(tsdf[0], tsdf[1], tsdf[2], tsdf[3]));
+        if (S.n_mirror) {  // sharded volume: the same 16 bytes into every rank's TSDF mirror (posted stores over NVLink)
+          const size_t slot = ((size_t)S.shard_rank * S.mirror_stride + idx) * kBlockVolume + lane * 4 + slab * 128;
+          for (int r = 0; r < S.n_mirror; ++r) st16(S.mirror[r] + slot, make_float4(tsdf[0], tsdf[1], tsdf[2], tsdf[3]));
+        }
         st16u(base_rgbw + slab * 128, make_uint4(rgbw[0], rgbw[1], rgbw[2], rgbw[3]));
         st16(base_logit + slab * 128, make_float4(logit[0], logit[1], logit[2], logit[3]));
       }

@@ -148,21 +148,26 @@ void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& 
 // ray march
 // ------------------------------------------------------------------------------------------
 struct Grid { int ox, oy, oz, nx, ny, nz, shift; const int* cells; };
-struct BlockCache { int bx, by, bz; const unsigned char* base; };  // bx = INT_MIN: nothing cached; base = null: absent
+struct BlockCache { int bx, by, bz; int entry; };  // bx = INT_MIN: nothing cached; entry < 0: absent
 
-// Where the voxels of a block live.  Local: this engine's table and pool.  Shared: the table and pool of the shard
-// that owns the block coordinate (owner_of), reached through peer-mapped pointers -- NVLink loads inside the march.
+// Where the voxels of a block live.  A block is named by its ENTRY: the pool index (local volume), or owner shard
+// << kIndexShardShift | pool index (sharded volume) -- exactly what the map's occupied cells hold.
+//   tsdf(entry)   the block's TSDF plane, all the march and the gradient need
+//   block(entry)  the block itself, for the colour / logit of the one hit voxel
+// Local: this engine's table and pool.  Shared: the pool of the shard that owns the block, reached through peer-mapped
+// pointers (NVLink loads inside the march) -- or, when the shards keep TSDF mirrors, a LOCAL copy of every shard's
+// TSDF planes that the owners' integrate kernels keep up to date with posted NVLink stores (tsdf_device.cuh).
 template <bool SHARED> struct Volume;
 template <> struct Volume<false> {
   DeviceState S;
-  __device__ __forceinline__ const unsigned char* at(int entry) const { return S.voxels + (size_t)entry * kBlockBytes; }
-  __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
-    const int idx = table_find(S, pack_key(bx, by, bz));
-    return idx < 0 ? nullptr : S.voxels + (size_t)idx * kBlockBytes;
-  }
+  __device__ __forceinline__ const unsigned char* block(int entry) const { return S.voxels + (size_t)entry * kBlockBytes; }
+  __device__ __forceinline__ const float* tsdf(int entry) const { return reinterpret_cast<const float*>(block(entry)); }
+  __device__ __forceinline__ int find_entry(int bx, int by, int bz) const { return table_find(S, pack_key(bx, by, bz)); }
 };
 template <> struct Volume<true> {
   const PeerView* shards; int n_shards, shard_shift;
+  const unsigned char* pool[kMaxPeers];    // every shard's voxel pool (peer-mapped): kernel parameters, not a load per sample
+  const float* mirror; int mirror_stride;  // local TSDF mirror of all shards ([shard][pool index][512]) or null
   // Fused exchange of the results: when n_out > 0 every ray's pixel is stored into the image buffers of ALL ranks
   // (peer-mapped pointers, posted stores over NVLink issued as the rays finish) instead of into one local image that an
   // all-gather would have to distribute afterwards.
@@ -170,17 +175,20 @@ template <> struct Volume<true> {
   // which 8-row tiles this launch renders: tile_first, tile_first + tile_stride, ...  (stride 1 = a contiguous band;
   // stride = number of ranks interleaves the tiles of a view over the ranks, so that all of them finish together)
   int tile_stride;
-  __device__ __forceinline__ const unsigned char* at(int entry) const {  // owner shard in the top bits: no table probe over NVLink
-    return shards[entry >> kIndexShardShift].voxels + (size_t)(entry & ((1 << kIndexShardShift) - 1)) * kBlockBytes;
+  __device__ __forceinline__ const unsigned char* block(int entry) const {  // owner shard in the top bits: no table probe over NVLink
+    return pool[entry >> kIndexShardShift] + (size_t)(entry & ((1 << kIndexShardShift) - 1)) * kBlockBytes;
   }
-  __device__ __forceinline__ const unsigned char* find(int bx, int by, int bz) const {
+  __device__ __forceinline__ const float* tsdf(int entry) const {
+    if (mirror) return mirror + ((size_t)(entry >> kIndexShardShift) * mirror_stride + (entry & ((1 << kIndexShardShift) - 1))) * kBlockVolume;
+    return reinterpret_cast<const float*>(block(entry));
+  }
+  __device__ __forceinline__ int find_entry(int bx, int by, int bz) const {
     const u64 key = pack_key(bx, by, bz);
-    const PeerView& v = shards[owner_of(key, n_shards, shard_shift)];
-    const int idx = table_find_in(v.table, v.table_mask, key);
-    return idx < 0 ? nullptr : v.voxels + (size_t)idx * kBlockBytes;
+    const int r = (int)owner_of(key, n_shards, shard_shift);
+    const int idx = table_find_in(shards[r].table, shards[r].table_mask, key);
+    return idx < 0 ? -1 : ((r << kIndexShardShift) | idx);
   }
 };
-__device__ __forceinline__ const float* base_tsdf(const unsigned char* b) { return reinterpret_cast<const float*>(b); }
 __device__ __forceinline__ const uint32_t* base_rgbw(const unsigned char* b) { return reinterpret_cast<const uint32_t*>(b + kPlaneBytes); }
 __device__ __forceinline__ const float* base_logit(const unsigned char* b) { return reinterpret_cast<const float*>(b + 2 * kPlaneBytes); }
 
@@ -217,16 +225,12 @@ __device__ __forceinline__ int cell_value(const Grid& G, int bx, int by, int bz,
 template <bool CLAMP>
 __device__ __forceinline__ int nearest_voxel(float f) { return CLAMP ? round_to_voxel(f) : __float2int_rz(roundf(f)); }
 
-// voxels of block (bx, by, bz) or null: straight from the dense entry when one cell is one block (the usual case),
-// through the owner's hash table otherwise
-template <bool DENSE, class V>
-__device__ __forceinline__ const unsigned char* block_of(const V& vol, const Grid& G, int g, int bx, int by, int bz) {
-  return DENSE ? vol.at(g) : vol.find(bx, by, bz);
-}
+// entry of block (bx, by, bz) or -1: straight from the map cell when one cell is one block (the usual case), through the
+// owner's hash table otherwise
 template <class V>
-__device__ __forceinline__ const unsigned char* block_or_null(const V& vol, const Grid& G, int bx, int by, int bz) {
-  if (G.shift == 0) { const int g = cell_value<true>(G, bx, by, bz); return g >= 0 ? vol.at(g) : nullptr; }
-  return cell_value<false>(G, bx, by, bz) >= 0 ? vol.find(bx, by, bz) : nullptr;
+__device__ __forceinline__ int block_entry(const V& vol, const Grid& G, int bx, int by, int bz) {
+  if (G.shift == 0) { const int g = cell_value<true>(G, bx, by, bz); return g >= 0 ? g : -1; }
+  return cell_value<false>(G, bx, by, bz) >= 0 ? vol.find_entry(bx, by, bz) : -1;
 }
 
 template <class V>
@@ -234,15 +238,15 @@ __device__ __forceinline__ void cache_lookup(const V& vol, const Grid& G, BlockC
   const int bx = px >> 3, by = py >> 3, bz = pz >> 3;
   if ((bx ^ c.bx) | (by ^ c.by) | (bz ^ c.bz)) {
     c.bx = bx; c.by = by; c.bz = bz;
-    c.base = block_or_null(vol, G, bx, by, bz);
+    c.entry = block_entry(vol, G, bx, by, bz);
   }
 }
 // Retrieve<VoxelTSDF>: absent -> VoxelTSDF() == +1 (voxel_types.cu:8)
 template <class V>
 __device__ __forceinline__ float fetch_tsdf(const V& vol, const Grid& G, BlockCache& c, int px, int py, int pz) {
   cache_lookup(vol, G, c, px, py, pz);
-  if (!c.base) return 1.f;
-  return __ldg(base_tsdf(c.base) + voxel_index(px, py, pz));
+  if (c.entry < 0) return 1.f;
+  return __ldg(vol.tsdf(c.entry) + voxel_index(px, py, pz));
 }
 template <bool CLAMP, class V>
 __device__ __forceinline__ float fetch_tsdf_f(const V& vol, const Grid& G, BlockCache& c, float3 p) {
@@ -264,8 +268,8 @@ __device__ __forceinline__ float march_sample(const V& vol, const Grid& G, float
   skip = 0;
   float t = 1.f;
   if (g >= 0) {
-    const unsigned char* base = block_of<DENSE>(vol, G, g, bx, by, bz);
-    if (DENSE || base) t = __ldg(base_tsdf(base) + voxel_index(px, py, pz));
+    const int entry = DENSE ? g : vol.find_entry(bx, by, bz);
+    if (DENSE || entry >= 0) t = __ldg(vol.tsdf(entry) + voxel_index(px, py, pz));
   } else if (g == kEscaped) {
     skip = kEscaped;  // the ray has left the volume for good
   } else if (g <= -2) {
@@ -325,8 +329,12 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
   const int y = row0 + (SHARED ? (int)blockIdx.y * tile_stride_of(vol) : (int)blockIdx.y) * 8 + (warp >> 2) * 4 + (lane >> 3);
-  if (x >= P.w || y >= P.h || y >= row0 + rows) return;
+  const bool in_image = x < P.w && y < P.h && y < row0 + rows;
+  if (!SHARED && !in_image) return;  // (the shared variant keeps every thread: its CTAs store their tile together)
   const int idx = y * P.w + x;
+  uint32_t out_rgba = 0u, out_normal = 0u;  // r | g << 8 | b << 16 | a << 24; a miss is (0, 0, 0, 0) like the reference
+  float out_depth = CUDART_INF_F;
+  if (in_image) {
   Grid G;
   G.ox = M.hdr[0]; G.oy = M.hdr[1]; G.oz = M.hdr[2]; G.nx = M.hdr[3]; G.ny = M.hdr[4]; G.nz = M.hdr[5]; G.shift = M.hdr[6];
   G.cells = M.cells;
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   const float smax = fmaxf(fmaxf(fabsf(ray_step_grid.x), fabsf(ray_step_grid.y)), fabsf(ray_step_grid.z));
   const float inv_smax = 1.f / (smax * 1.001f + 1e-6f);
 
-  BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.base = nullptr;
+  BlockCache cache; cache.bx = cache.by = cache.bz = (int)0x80000000; cache.entry = -1;
   // sides of the block AABB this ray can only move away from (see cell_distance)
   const unsigned leaving = (ray_step_grid.x <= 0.f ? 1u : 0u) | (ray_step_grid.y <= 0.f ? 2u : 0u) | (ray_step_grid.z <= 0.f ? 4u : 0u) |
                            (ray_step_grid.x >= 0.f ? 8u : 0u) | (ray_step_grid.y >= 0.f ? 16u : 0u) | (ray_step_grid.z >= 0.f ? 32u : 0u);
@@ -367,9 +375,6 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
   const f32x2 sxy = pack2(ray_step_grid.x, ray_step_grid.y);
   float pz = pos_grid.z;
   const float sz = ray_step_grid.z;
-
-  uint32_t out_rgba = 0u, out_normal = 0u;  // r | g << 8 | b << 16 | a << 24; a miss is (0, 0, 0, 0) like the reference
-  float out_depth = CUDART_INF_F;
 
   const bool hit = G.shift == 0 ? march<CLAMP, true>(vol, G, pxy, pz, sxy, sz, inv_smax, leaving, max_step)
                                 : march<CLAMP, false>(vol, G, pxy, pz, sxy, sz, inv_smax, leaving, max_step);
@@ -391,33 +396,34 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
     }
     const int fx = nearest_voxel<CLAMP>(mid.x), fy = nearest_voxel<CLAMP>(mid.y), fz = nearest_voxel<CLAMP>(mid.z);
     cache_lookup(vol, G, cache, fx, fy, fz);
-    const unsigned char* const cbase = cache.base;
+    const int centry = cache.entry;
     // Block of each of the 6 neighbours first (only a neighbour across a block face needs a table lookup,
     // at most one per axis), then all 8 voxel loads of the hit -- colour, logit and the 6 gradient samples -- are
     // independent and in flight together (voxel_tsdf.cu:277-291; short arithmetic wraps like the reference).
     const int nx[6] = {(short)(fx + 1), (short)(fx - 1), fx, fx, fx, fx};
     const int ny[6] = {fy, fy, (short)(fy + 1), (short)(fy - 1), fy, fy};
     const int nz[6] = {fz, fz, fz, fz, (short)(fz + 1), (short)(fz - 1)};
-    const unsigned char* nbase[6];
+    int nentry[6];
 #pragma unroll
     for (int n = 0; n < 6; ++n) {
-      nbase[n] = cbase;
+      nentry[n] = centry;
       if (((nx[n] ^ fx) | (ny[n] ^ fy) | (nz[n] ^ fz)) >> 3) {  // different block coordinate
         const int bx = nx[n] >> 3, by = ny[n] >> 3, bz = nz[n] >> 3;
-        nbase[n] = block_or_null(vol, G, bx, by, bz);
+        nentry[n] = block_entry(vol, G, bx, by, bz);
       }
     }
     uint32_t rgbw = 0u;  // VoxelRGBW() / VoxelSEGM() defaults for an absent voxel (voxel_types.cu:3,11)
     float lgt = 0.f;
-    if (cbase) {
+    if (centry >= 0) {
       const int k = voxel_index(fx, fy, fz);
+      const unsigned char* const cbase = vol.block(centry);
       rgbw = __ldg(base_rgbw(cbase) + k);
       lgt = __ldg(base_logit(cbase) + k);
     }
     float gv[6];
 #pragma unroll
-    for (int n = 0; n < 6; ++n) gv[n] = nbase[n] ? __ldg(base_tsdf(nbase[n]) + voxel_index(nx[n], ny[n], nz[n])) : 1.f;
-    const float prob = cbase ? logit_to_prob(lgt) : 0.f;
+    for (int n = 0; n < 6; ++n) gv[n] = nentry[n] >= 0 ? __ldg(vol.tsdf(nentry[n]) + voxel_index(nx[n], ny[n], nz[n])) : 1.f;
+    const float prob = centry >= 0 ? logit_to_prob(lgt) : 0.f;
     const float gxp = gv[0], gxn = gv[1], gyp = gv[2], gyn = gv[3], gzp = gv[4], gzn = gv[5];
     const float3 nrm = f3(gxp - gxn, gyp - gyn, gzp - gzn);
     const float3 neg_dir = f3(-ray_dir_world.x, -ray_dir_world.y, -ray_dir_world.z);
@@ -431,16 +437,30 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
     const float3 pc = apply(P.cam_T_world, f3(mid.x * P.voxel_size, mid.y * P.voxel_size, mid.z * P.voxel_size));
     out_depth = pc.z;
   }
+  }  // in_image
 
   if constexpr (SHARED) {
     if (vol.n_out > 0) {
-      for (int r = 0; r < vol.n_out; ++r) {
-        if (vol.out_rgba[r]) reinterpret_cast<uint32_t*>(vol.out_rgba[r])[idx] = out_rgba;
-        if (vol.out_normal[r]) reinterpret_cast<uint32_t*>(vol.out_normal[r])[idx] = out_normal;
-        if (vol.out_depth[r]) vol.out_depth[r][idx] = out_depth;
+      // The CTA's 32 x 8 tile goes out together: staged in shared memory in image order, then each warp stores one row
+      // of 32 pixels = 128 contiguous bytes per image and destination -- four times fewer, four times larger NVLink
+      // packets than 8-pixel segments stored ray by ray.
+      __shared__ uint32_t s_rgba[256], s_normal[256];
+      __shared__ float s_depth[256];
+      const int tx = (warp & 3) * 8 + (lane & 7), ty = (warp >> 2) * 4 + (lane >> 3);
+      s_rgba[ty * 32 + tx] = out_rgba; s_normal[ty * 32 + tx] = out_normal; s_depth[ty * 32 + tx] = out_depth;
+      __syncthreads();
+      const int ox = blockIdx.x * 32 + lane, oy = y - ty + warp;  // warp w stores row w of the tile
+      if (ox < P.w && oy < P.h && oy < row0 + rows) {
+        const int o = oy * P.w + ox, t = warp * 32 + lane;
+        for (int r = 0; r < vol.n_out; ++r) {
+          if (vol.out_rgba[r]) reinterpret_cast<uint32_t*>(vol.out_rgba[r])[o] = s_rgba[t];
+          if (vol.out_normal[r]) reinterpret_cast<uint32_t*>(vol.out_normal[r])[o] = s_normal[t];
+          if (vol.out_depth[r]) vol.out_depth[r][o] = s_depth[t];
+        }
       }
       return;
     }
+    if (!in_image) return;
   }
   if (img_rgba) reinterpret_cast<uint32_t*>(img_rgba)[idx] = out_rgba;
   if (img_normal) reinterpret_cast<uint32_t*>(img_normal)[idx] = out_normal;
@@ -473,9 +493,10 @@ void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size,
 // Rows [row0, row0 + rows) of a view over a volume sharded across `n_shards` engines whose tables and pools are
 // mapped in `shards` (device array): bit-identical to the single-volume render, voxels of foreign blocks are read
 // from their owner over NVLink.
-void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
-                           const SkipMap& M, int row0, int rows, int tile_stride, uchar4* rgba, uchar4* normal, float* hit_depth,
-                           int n_out, void* const* out_rgba, void* const* out_normal, void* const* out_depth, cudaStream_t st) {
+void launch_raycast_shared(const PeerView* shards, const PeerView* host_shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
+                           const SkipMap& M, int row0, int rows, int tile_stride, const float* mirror, int mirror_stride, uchar4* rgba,
+                           uchar4* normal, float* hit_depth, int n_out, void* const* out_rgba, void* const* out_normal,
+                           void* const* out_depth, cudaStream_t st) {
   if (rows <= 0) return;
   // tile_stride > 1: `rows` bounds the rows of the image this launch may touch ([row0, row0 + rows)), of which it
   // renders every tile_stride-th 8-row tile starting at row0
@@ -485,6 +506,8 @@ void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift
   Volume<true> vol; vol.shards = shards; vol.n_shards = n_shards; vol.shard_shift = shard_shift;
   vol.n_out = n_out;
   vol.tile_stride = tile_stride;
+  vol.mirror = mirror; vol.mirror_stride = mirror_stride;
+  for (int r = 0; r < kMaxPeers; ++r) vol.pool[r] = r < n_shards ? host_shards[r].voxels : nullptr;
   for (int r = 0; r < kMaxPeers; ++r) {
     vol.out_rgba[r] = r < n_out && out_rgba ? (uchar4*)out_rgba[r] : nullptr;
     vol.out_normal[r] = r < n_out && out_normal ? (uchar4*)out_normal[r] : nullptr;

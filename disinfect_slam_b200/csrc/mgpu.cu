@@ -83,6 +83,10 @@ struct tsdf_mgpu {
   int epoch = 0;                            // barrier count (identical on all ranks: same call sequence)
   int* d_err = nullptr;                     // set by a barrier that timed out
   bool fused = true;
+  int views_since_integrate = 0;            // all ranks make the same calls: > 0 means no shard has integrated since the last view
+  // TSDF mirror of this rank: every shard's TSDF planes, kept up to date by the owners' integrate kernels (tsdf_mirror_attach)
+  float* mirror = nullptr;
+  void* mopened[kMaxRanks] = {};
   int last_w = 0, last_h = 0;
   unsigned long long* keys = nullptr; size_t keys_cap = 0;
   long long* d_sizes = nullptr; long long* h_sizes = nullptr;  // [world] gather sizes / counter sums
@@ -141,7 +145,7 @@ __global__ void peer_barrier_kernel(PeerFlags peers, int rank, int world, int ep
   }
 }
 
-struct XBlob { cudaIpcMemHandle_t h; long long pid; void* raw; int device; int pad; };
+struct XBlob { cudaIpcMemHandle_t h; cudaIpcMemHandle_t hm; long long pid; void* raw; void* raw_mirror; int device; int pool_blocks; };
 }  // namespace
 
 extern "C" {
@@ -170,7 +174,8 @@ int tsdf_mgpu_destroy(tsdf_mgpu_handle m) {
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
   for (int r = 0; r < kMaxRanks; ++r) if (m->xopened[r]) cudaIpcCloseMemHandle(m->xopened[r]);
-  cudaFree(m->xbuf); cudaFree(m->d_err);
+  for (int r = 0; r < kMaxRanks; ++r) if (m->mopened[r]) cudaIpcCloseMemHandle(m->mopened[r]);
+  cudaFree(m->xbuf); cudaFree(m->d_err); cudaFree(m->mirror);
   cudaFree(m->d_flag); cudaFree(m->keys); cudaFree(m->d_sizes); cudaFree(m->gather_all);
   if (m->h_sizes) cudaFreeHost(m->h_sizes);
   collect(m);
@@ -248,10 +253,19 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
     {
       const char* ex = getenv("TSDF_MGPU_EXCHANGE");
       m->fused = !(ex && !strcmp(ex, "nccl"));
+      const char* mi = getenv("TSDF_MGPU_MIRROR");
+      const bool want_mirror = world > 1 && !(mi && !strcmp(mi, "0"));
       std::vector<XBlob> xb(world);
       XBlob mine{};
       CU(cudaIpcGetMemHandle(&mine.h, m->xbuf));
-      mine.pid = (long long)getpid(); mine.raw = m->xbuf; mine.device = m->device;
+      mine.pid = (long long)getpid(); mine.raw = m->xbuf; mine.device = m->device; mine.pool_blocks = cfg.pool_blocks;
+      if (want_mirror) {  // all shards use the same pool size here, so every rank sizes its mirror alike
+        const size_t bytes = (size_t)world * cfg.pool_blocks * 2048;
+        CU(cudaMalloc(&m->mirror, bytes));
+        CU(cudaMemsetAsync(m->mirror, 0, bytes, m->es));
+        CU(cudaIpcGetMemHandle(&mine.hm, m->mirror));
+        mine.raw_mirror = m->mirror;
+      }
       XBlob* d_xb = nullptr;
       CU(cudaMalloc(&d_xb, sizeof(XBlob) * world));
       CU(cudaMemcpyAsync(d_xb + rank, &mine, sizeof(XBlob), cudaMemcpyHostToDevice, m->es));
@@ -273,6 +287,16 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
           CU(cudaIpcOpenMemHandle(&p, xb[r].h, cudaIpcMemLazyEnablePeerAccess));
           m->xopened[r] = p; m->xpeer[r] = (unsigned char*)p;
         }
+      }
+      if (want_mirror) {
+        void* mp[kMaxRanks] = {};
+        for (int r = 0; r < world; ++r) {
+          if (xb[r].pool_blocks != cfg.pool_blocks) return fail(TSDF_E_INVALID, "TSDF mirrors need the same pool_blocks on every rank (%d vs %d)", xb[r].pool_blocks, cfg.pool_blocks);
+          if (r == rank) mp[r] = m->mirror;
+          else if (xb[r].pid == (long long)getpid()) mp[r] = xb[r].raw_mirror;  // peer access was enabled above
+          else { CU(cudaIpcOpenMemHandle(&mp[r], xb[r].hm, cudaIpcMemLazyEnablePeerAccess)); m->mopened[r] = mp[r]; }
+        }
+        TS(tsdf_mirror_attach(m->eng, world, mp, cfg.pool_blocks));
       }
       // nobody may signal into a buffer that its owner is still clearing
       NC(ncclAllReduce(m->d_flag, m->d_flag, 1, ncclInt, ncclSum, m->comm_sync, m->es));
@@ -331,6 +355,7 @@ int tsdf_mgpu_integrate(tsdf_mgpu_handle m, int root, int on_device, const void*
   if (rc == TSDF_E_INVALID || rc == TSDF_E_CUDA || rc == TSDF_E_NO_DEVICE) return fail(rc, "tsdf_integrate_device: %s", tsdf_last_error());
   CU(cudaEventRecord(s.consumed, m->es));
   s.used = true;
+  m->views_since_integrate = 0;
   m->cur = (m->cur + 1) % kStage;
   if (rc != TSDF_OK) return fail(rc, "%s", tsdf_last_error());  // exhaustion of an earlier frame; this frame was enqueued
   return TSDF_OK;
@@ -370,7 +395,8 @@ int tsdf_mgpu_raycast(tsdf_mgpu_handle m, float max_depth, int w, int h, const f
       void* o[3][kMaxRanks];
       for (int i = 0; i < 3; ++i) for (int r = 0; r < m->world; ++r) o[i][r] = m->xpeer[r] + (size_t)i * m->img_stride;
       // 8-row tiles dealt out round-robin: every rank renders the same mix of rows
-      TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, m->rank, m->world, m->world, o[0], o[1], o[2]));
+      TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, m->rank, m->world, m->views_since_integrate > 0 ? 1 : 0, m->world, o[0], o[1], o[2]));
+      m->views_since_integrate++;
     }
     { Timed tm(m, T_ALLGATHER, m->es); int rc2 = peer_barrier(m); if (rc2) return rc2; }
   } else {

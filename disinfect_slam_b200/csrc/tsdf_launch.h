@@ -16,9 +16,10 @@ void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const in
 // kernels_raycast.cu
 void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int gen, bool lazy, int num_sms,
                            cudaStream_t st);
-void launch_raycast_shared(const PeerView* shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
-                           const SkipMap& M, int row0, int rows, int tile_stride, uchar4* rgba, uchar4* normal, float* hit_depth,
-                           int n_out, void* const* out_rgba, void* const* out_normal, void* const* out_depth, cudaStream_t st);
+void launch_raycast_shared(const PeerView* shards, const PeerView* host_shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
+                           const SkipMap& M, int row0, int rows, int tile_stride, const float* mirror, int mirror_stride, uchar4* rgba,
+                           uchar4* normal, float* hit_depth, int n_out, void* const* out_rgba, void* const* out_normal,
+                           void* const* out_depth, cudaStream_t st);
 void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, const SkipMap& M, uchar4* rgba,
                     uchar4* normal, float* hit_depth, unsigned long long* packed_keys, cudaStream_t st);
 

@@ -199,11 +199,24 @@ int tsdf_raycast_shared(tsdf_handle h, float max_depth, int width, int height, c
  * whole arrays may be NULL) -- posted stores over NVLink while the march runs, instead of a local image plus an
  * all-gather afterwards.  The launch renders the 8-row tiles tile_first, tile_first + tile_stride, ... of the view:
  * with tile_first = rank and tile_stride = number of ranks the tiles of a view are dealt out round-robin, so every rank
- * gets the same mix of cheap and expensive rows and all of them finish together.  The caller orders the destinations'
- * readers with its own barrier. */
+ * gets the same mix of cheap and expensive rows and all of them finish together.  peers_unchanged != 0: the caller
+ * vouches that no shard has integrated since this engine's previous shared view (then not even the map-maintenance
+ * kernels, which would find nothing to do, are launched).  The caller orders the destinations' readers with its own
+ * barrier. */
 int tsdf_raycast_shared_scatter(tsdf_handle h, float max_depth, int width, int height, const float K[4],
-                                const float q_xyzw[4], const float t_xyz[3], int tile_first, int tile_stride, int n_dest,
-                                void* const* d_rgba, void* const* d_normal, void* const* d_hit_depth);
+                                const float q_xyzw[4], const float t_xyz[3], int tile_first, int tile_stride,
+                                int peers_unchanged, int n_dest, void* const* d_rgba, void* const* d_normal,
+                                void* const* d_hit_depth);
+
+/* TSDF mirrors for a sharded volume (optional; call on an idle engine, before the first frame).  mirrors[r] = rank r's
+ * mirror buffer as this GPU addresses it (peer-mapped; mirrors[shard_rank] is this engine's own): shard_count x
+ * stride_blocks x 512 floats, stride_blocks >= the largest pool of any shard.  From then on the integrate kernel stores
+ * every TSDF value it writes into slot [shard_rank][pool index] of ALL mirrors too (posted stores over NVLink, 16 bytes
+ * per updated voxel quad and rank), and tsdf_raycast_shared* reads every TSDF sample from the local mirror instead of
+ * from the owner's memory over NVLink; only the colour and probability of the hit voxel still come from the owner.
+ * It trades 2 KB per block of ANY shard on every GPU (a third of the voxel data, replicated) for a march without remote
+ * loads.  world == 0 detaches.  Blocks written through tsdf_assign_voxels are not mirrored. */
+int tsdf_mirror_attach(tsdf_handle h, int world, void* const* mirrors, int stride_blocks);
 
 /* TSDFGrid::GatherValid()                               utils/tsdf/voxel_tsdf.cu:399-425
  * TSDFGrid::GatherVoxels(BoundingCube<float>)           utils/tsdf/voxel_tsdf.cu:427-454

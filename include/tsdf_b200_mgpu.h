@@ -25,6 +25,12 @@
  *               so the image is bit-identical to a single-GPU render -- and one grouped in-place ncclAllGather
  *               assembles the three images on every rank (it is also the barrier before the next Integrate).
  *
+ *   TSDF mirrors (default; TSDF_MGPU_MIRROR=0 turns them off): every rank also holds a copy of every shard's TSDF planes
+ *               (2 KB per block), which the owners' integrate kernels keep current with posted NVLink stores
+ *               (tsdf_mirror_attach).  The march then reads every TSDF sample locally; only the colour and probability of
+ *               a hit voxel are fetched from the owner.  Without mirrors a rank's memory holds just its shard (capacity
+ *               scales with the GPUs) and the march loads foreign voxels over NVLink sample by sample.
+ *
  * Status codes are those of tsdf_b200.h; tsdf_mgpu_last_error() describes the last failure of the calling thread.
  */
 #ifndef TSDF_B200_MGPU_H_
