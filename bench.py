@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded single-stream leg at N > 1")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE configs 1, 3, 4, 5 legs")
+    ap.add_argument("--no-config15", action="store_true", help="skip the config 1 / config 5 legs (development runs)")
     ap.add_argument("--config1-frames", type=int, default=100)
     ap.add_argument("--rooms", type=int, default=0, help="config 3: rooms of the synthetic floor (each = one lap of the config-2 frames); 0 = as many as ~50 M active voxels take")
     ap.add_argument("--views", type=int, default=16, help="config 4: 1920x1080 virtual views per batch")
@@ -702,7 +703,7 @@ def main():
             import traceback
             extra["config3"] = {"error": repr(ex), "trace": traceback.format_exc()[-800:]}
         try:
-            if stream1 is not None:
+            if stream1 is not None and not args.no_config15:
                 extra["config1"], extra["config5"] = bench_legs.config1_and_5(args, stream1, rank, world, local_rank, dev, dist if world > 1 else None)
         except Exception as ex:
             import traceback

@@ -212,13 +212,15 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
 
     pool_rank = int(pool_total / world * 1.5)
     n_hist = n_tour + W + K
-    frames = mgpu.make_frames([cams[s % n_tour] for s in range(n_hist + 2 * K)],
-                              [planes(s) for s in range(n_hist + 2 * K)] if rank == 0 else None)
+    frames = mgpu.make_frames([cams[s % n_tour] for s in range(n_hist + 3 * K)],
+                              [planes(s) for s in range(n_hist + 3 * K)] if rank == 0 else None)
     import os
 
-    def make_volume(exchange, mirror=True):
+    def make_volume(exchange="fused", mirror="pull", alloc="exchange", tiles="interleave"):
         os.environ["TSDF_MGPU_EXCHANGE"] = exchange  # read by tsdf_mgpu_create
-        os.environ["TSDF_MGPU_MIRROR"] = "1" if mirror else "0"
+        os.environ["TSDF_MGPU_MIRROR"] = mirror
+        os.environ["TSDF_MGPU_ALLOC"] = alloc
+        os.environ["TSDF_MGPU_TILES"] = tiles
         return mgpu.ShardedVolume(VOXEL3, TRUNC3, rank, world, fresh_id(), device=local_rank, pool_blocks=pool_rank,
                                   table_slots=max(1 << 16, 1 << int(np.ceil(np.log2(4 * pool_rank)))), max_image_pixels=big, shard_shift=2)
 
@@ -240,7 +242,7 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
 
     per = lambda m, n, k: (1e3 * m[k] / n[k]) if n[k] else None  # noqa: E731
     # the conventional exchange first (NCCL barrier + local image + all-gather), for comparison only
-    vol = make_volume("nccl")
+    vol = make_volume("nccl", mirror="0", alloc="owner")
     tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
     seq(0, n_tour, 0)
     seq(n_tour, W, 1)
@@ -250,8 +252,9 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     nccl_variant = {"frames_per_s": K / (ms_n * 1e-3), "us_per_frame": 1e3 * ms_n / K, "barrier_allreduce_us": per(cms_n, cn_n, "barrier"),
                     "image_allgather_us": per(cms_n, cn_n, "allgather"), "raycast_shared_kernels_us": per(cms_n, cn_n, "raycast_shared"),
                     "exchange": "TSDF_MGPU_EXCHANGE=nccl: 4-byte ncclAllReduce, march into a local image, grouped in-place ncclAllGather of 12 B/px"}
-    # fused exchange, but every TSDF sample of a foreign block loaded over NVLink (no mirrors): memory per rank = its shard only
-    vol = make_volume("fused", mirror=False)
+    # fused exchange in its first form: 8-row tiles dealt round-robin, every TSDF sample of a foreign block loaded over NVLink,
+    # every rank walks all pixel rays in the allocation pass
+    vol = make_volume("fused", mirror="0", alloc="owner")
     tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
     seq(0, n_tour, 0)
     seq(n_tour, W, 1)
@@ -260,10 +263,23 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     barrier(torch, dist, world)
     nomirror_variant = {"frames_per_s": K / (ms_m * 1e-3), "us_per_frame": 1e3 * ms_m / K, "peer_barrier_before_march_us": per(cms_m, cn_m, "barrier"),
                         "march_with_fused_scatter_us": per(cms_m, cn_m, "raycast_shared"), "peer_barrier_after_march_us": per(cms_m, cn_m, "allgather"),
-                        "exchange": "TSDF_MGPU_MIRROR=0: fused exchange, foreign voxels loaded from their owner over NVLink sample by sample"}
-    # the product path: exchange fused into the march kernel, peer barriers instead of collectives, TSDF mirrors kept current
-    # by the integrate kernels
-    vol = make_volume("fused")
+                        "exchange": "TSDF_MGPU_MIRROR=0 TSDF_MGPU_ALLOC=owner: fused exchange with round-robin tiles, foreign voxels loaded from their owner "
+                                    "over NVLink sample by sample, allocation pass replicated on every rank"}
+    # the product path with one contiguous band of rows per rank instead of round-robin tiles
+    vol = make_volume(tiles="band")
+    tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
+    seq(0, n_tour, 0)
+    seq(n_tour, W, 1)
+    ms_b, cms_b, cn_b, _, _ = timed(n_tour + W, K, 1)
+    vol.close()
+    barrier(torch, dist, world)
+    band_variant = {"frames_per_s": K / (ms_b * 1e-3), "us_per_frame": 1e3 * ms_b / K, "peer_barrier_before_march_us": per(cms_b, cn_b, "barrier"),
+                    "march_with_fused_scatter_us": per(cms_b, cn_b, "raycast_shared"), "peer_barrier_after_march_us": per(cms_b, cn_b, "allgather"),
+                    "exchange": "TSDF_MGPU_TILES=band: as the product path, but rank r renders rows [r H/N, (r+1) H/N): fewer foreign blocks to fetch, "
+                                "uneven finishing times"}
+    # the product path: allocation pass sharded by image tiles (candidate keys mailed to their owners), one band of rows per
+    # rank marched over a pulled TSDF cache, rows stored into every rank's images, peer barriers instead of collectives
+    vol = make_volume()
     tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
     seq(0, n_tour, 0)          # the tour that builds the volume
     seq(n_tour, W, 1)          # warm-up with views
@@ -282,9 +298,26 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
         parity = "bit-exact" if bad == 0 and n_ref == n_act else f"MISMATCH: {bad} differing bytes, blocks {n_act} vs {n_ref}"
         ref.close()
     barrier(torch, dist, world)
-    ms_int, cms_i, cn_i, tot_i, _ = timed(n_hist, K, 0)
-    ms_cmp, cms_c, cn_c, _, _ = timed(n_hist + K, K, 2)
-    coll = {"frame_broadcast_us": per(cms, cn, "broadcast"), "peer_barrier_before_march_us": per(cms, cn, "barrier"),
+    # where a frame's time goes on this rank's engine stream: a second pass over the same frames with the engine's own phase
+    # timers on (not the timed run: the extra event records cost a few microseconds per frame)
+    L0 = tsdf_grid._lib.lib()
+    tsdf_grid._lib.check(L0.tsdf_set_profiling(vol.engine, 1))
+    seq(n_tour + W, K, 1)
+    vol.synchronize()
+    import ctypes as C
+    pms, pcnt = (C.c_float * 6)(), (C.c_int64 * 6)()
+    tsdf_grid._lib.check(L0.tsdf_get_phase_ms(vol.engine, pms, pcnt))
+    fetched = C.c_int64(0)
+    tsdf_grid._lib.check(L0.tsdf_shared_cache_stats(vol.engine, C.byref(fetched)))
+    tsdf_grid._lib.check(L0.tsdf_set_profiling(vol.engine, 0))
+    phases = {n: (1e3 * pms[i] / pcnt[i] if pcnt[i] else None) for i, n in ((1, "stage_and_walk_rays_us"), (2, "insert_candidates_and_select_us"), (3, "integrate_us"),
+                                                                            (4, "map_fetch_march_scatter_us"))}
+    phases["tsdf_blocks_fetched_last_view"] = int(fetched.value)
+    phases["note"] = f"rank {rank}'s engine stream, CUDA events; the fetch moves 2 KB per block over NVLink"
+    ms_int, cms_i, cn_i, tot_i, _ = timed(n_hist + K, K, 0)
+    ms_cmp, cms_c, cn_c, _, _ = timed(n_hist + 2 * K, K, 2)
+    coll = {"frame_broadcast_us": per(cms, cn, "broadcast"), "peer_barrier_candidate_exchange_us": per(cms, cn, "exchange_barrier"),
+            "peer_barrier_before_march_us": per(cms, cn, "barrier"),
             "march_with_fused_scatter_us": per(cms, cn, "raycast_shared"), "peer_barrier_after_march_us": per(cms, cn, "allgather"),
             "composite_allreduce_us": per(cms_c, cn_c, "composite_allreduce"),
             "bytes": {"frame_broadcast": 15 * npx, "scattered_per_rank": 12 * ((H + world - 1) // world) * Wd * (world - 1), "composite_allreduce": 16 * npx},
@@ -297,20 +330,22 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                                                           "carries the frame planes once per ring hop plus its image rows to 7 peers, rx the peers' rows and the voxels "
                                                           "its march read from other shards"}
     on_path = {"frame_broadcast_us": coll["frame_broadcast_us"] or 0.0,
-               "peer_barriers_us": (coll["peer_barrier_before_march_us"] or 0.0) + (coll["peer_barrier_after_march_us"] or 0.0)}
+               "peer_barriers_us": (coll["peer_barrier_before_march_us"] or 0.0) + (coll["peer_barrier_after_march_us"] or 0.0) +
+                                   (coll["peer_barrier_candidate_exchange_us"] or 0.0)}
     res3.update({"active_voxels": 512 * n_act, "active_blocks": n_act, "sharded_parity": parity,
                  "integrate_raycast": {"frames_per_s": K / (ms_rc * 1e-3), "us_per_frame": 1e3 * ms_rc / K, "voxel_updates_per_s": tot["n_updated"] / (ms_rc * 1e-3),
                                        "raycast_mrays_per_s": K * npx / (ms_rc * 1e-3) / 1e6, "visible_blocks_per_frame": tot["n_visible"] / K},
                  "integrate_only": {"frames_per_s": K / (ms_int * 1e-3), "us_per_frame": 1e3 * ms_int / K, "voxel_updates_per_s": tot_i["n_updated"] / (ms_int * 1e-3),
                                     "broadcast_us": per(cms_i, cn_i, "broadcast")},
                  "integrate_raycast_min_composite": {"frames_per_s": K / (ms_cmp * 1e-3), "us_per_frame": 1e3 * ms_cmp / K},
-                 "collectives": coll, "limiting_collective": max(on_path, key=on_path.get), "nccl_exchange_variant": nccl_variant,
-                 "no_mirror_variant": nomirror_variant,
+                 "collectives": coll, "limiting_collective": max(on_path, key=on_path.get), "engine_phases": phases,
+                 "nccl_exchange_variant": nccl_variant, "round_robin_remote_loads_variant": nomirror_variant, "row_bands_variant": band_variant,
                  "path": "libtsdf_b200_mgpu.so: tsdf_mgpu_run_sequence (C++ loop, NCCL linked directly): grouped ncclBroadcast of the planes from rank 0's HBM, "
-                         "owner-filtered allocate + integrate (every updated TSDF value also stored into all ranks' TSDF mirrors), peer barrier kernel, "
-                         "tsdf_raycast_shared_scatter (each rank marches 1/N of the 8-row tiles, TSDF samples from its local mirror, hit colours from the "
-                         "owner over NVLink, and stores the finished rays into every rank's images), peer barrier kernel; CUDA events on the engine stream, max over ranks; voxel "
-                         "updates all-reduced"})
+                         "frame staged everywhere, pixel rays walked on 1/N of the 32x8 tiles per rank with the candidate keys mailed to their owners' inboxes "
+                         "(NVLink stores), peer barrier kernel (also closes the previous view), owners insert, select + integrate; peer barrier kernel, skip map "
+                         "from all shards' directories, fetch of the foreign TSDF planes this rank's band of rows can meet (bulk NVLink reads into a local cache), "
+                         "tsdf_raycast_shared_scatter (band of H/N rows, TSDF samples local, hit colours from the owner, finished rays stored into every "
+                         "rank's images); CUDA events on the engine stream, max over ranks; voxel updates all-reduced"})
     # config 4 on the sharded volume: exact (rows split) and min-composited (whole views per rank)
     for md in (4.0, 10.0):
         r = {}

@@ -61,7 +61,11 @@ SYMBOLS = {
     "tsdf_peer_attach_local": (_i32, [_vp, _i32, _vp]),
     "tsdf_raycast_shared": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tsdf_mirror_attach": (_i32, [_vp, _i32, _vp, _i32]),
-    "tsdf_raycast_shared_scatter": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "tsdf_raycast_shared_scatter": (_i32, [_vp, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "tsdf_shared_cache_attach": (_i32, [_vp, _i32, _i32]),
+    "tsdf_shared_cache_stats": (_i32, [_vp, C.POINTER(_i64)]),
+    "tsdf_alloc_exchange_bytes": (C.c_size_t, [_i32, _i32]),
+    "tsdf_alloc_exchange_attach": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "tsdf_gather_valid": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_in_bound": (_i32, [_vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "tsdf_gather_fetch": (_i32, [_vp, _vp, _i64]),

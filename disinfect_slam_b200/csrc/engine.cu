@@ -83,6 +83,11 @@ struct tsdf_engine {
   int* h_scalar = nullptr;  // pinned scratch (C_COUNT ints)
   unsigned char* bounce[2] = {nullptr, nullptr};  // pinned staging for large device -> pageable-host results (see copy_to_host)
   cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+  // pulled TSDF cache of a sharded volume (tsdf_shared_cache_attach)
+  float* cache = nullptr; int* cache_stamp = nullptr; int* cache_list = nullptr; int* cache_count = nullptr;
+  int cache_stride = 0, cache_epoch = 1, cache_serial = 0, cache_pad = 3;
+  // candidate exchange of a sharded volume (tsdf_alloc_exchange_attach)
+  int* xa_cursor = nullptr; tsdf_frame_hook xa_hook = nullptr; void* xa_user = nullptr; unsigned xa_frames = 0;
   int n_active = 0;         // host mirror after the last completed frame
   tsdf_counters last{};
   bool profiling = false;
@@ -176,10 +181,14 @@ static void next_serial(tsdf_engine* e) {
 // kernels of one frame, enqueued on the compute stream; no host synchronisation
 static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const FrameInput& in, FrameBuf& f) {
   next_serial(e);  // (the per-call counters are zero here: cleared by the previous frame's publish kernel / after_mutation)
+  if (e->S.xa_on) e->S.xa_parity = (int)(e->xa_frames++ & 1u);
   phase_begin(e, PH_ALLOC, e->stream);
   launch_frame_allocate(e->S, P, in, f.tex, e->stream);
   phase_end(e, PH_ALLOC, e->stream);
+  // candidate exchange: counts published + all ranks ordered by the data plane's hook, then the owner's inserts
+  if (e->S.xa_on) e->xa_hook(e->xa_user, (void*)e->stream, e->xa_cursor + e->S.xa_parity * 8, e->S.xa_parity);
   phase_begin(e, PH_SELECT, e->stream);
+  if (e->S.xa_on) launch_insert_candidates(e->S, P, e->stream);
   launch_select_visible(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, e->num_sms, e->stream);
   phase_end(e, PH_SELECT, e->stream);
   phase_begin(e, PH_INTEGRATE, e->stream);
@@ -223,6 +232,7 @@ static int retire_slot(tsdf_engine* e, int s) {
   // once carving or tsdf_delete_blocks has freed blocks)
   if (c[C_ERROR] & ERR_POOL) return fail(TSDF_E_POOL_EXHAUSTED, "voxel block pool exhausted (pool_blocks=%d): some blocks of a frame were not allocated", e->cfg.pool_blocks);
   if (c[C_ERROR] & ERR_TABLE) return fail(TSDF_E_TABLE_FULL, "hash table full (table_slots=%d): some blocks of a frame were not allocated", e->cfg.table_slots);
+  if (c[C_ERROR] & ERR_EXCHANGE) return fail(TSDF_E_EXCHANGE_FULL, "candidate exchange full (cap_keys=%d): some candidate blocks of a frame were dropped", e->S.xa_cap);
   return TSDF_OK;
 }
 // host wait for every outstanding tsdf_raycast_async copy
@@ -354,6 +364,7 @@ int tsdf_destroy(tsdf_handle e) {
   cudaFree(e->S.table); cudaFree(e->S.block_key); cudaFree(e->S.voxels); cudaFree(e->S.free_stack); cudaFree(e->S.ctr);
   cudaFree(e->visible); cudaFree(e->selected); cudaFree(e->mesh_out); cudaFree(e->mesh_counter);
   cudaFree(e->skip.dist); cudaFree(e->skip.scratch); cudaFree(e->skip.hdr); cudaFree(e->skip.cells);
+  cudaFree(e->cache); cudaFree(e->cache_stamp); cudaFree(e->cache_list); cudaFree(e->cache_count); cudaFree(e->xa_cursor);
   for (int r = 0; r < kMaxPeers; ++r) for (int k = 0; k < 4; ++k) if (e->ipc_opened[r][k]) cudaIpcCloseMemHandle(e->ipc_opened[r][k]);
   cudaFree(e->d_self); cudaFree(e->d_peers);
   for (int i = 0; i < 2; ++i) {
@@ -771,8 +782,21 @@ static int raycast_shared_impl(tsdf_engine* e, float max_depth, int w, int h, co
     launch_build_skip_map(e->d_peers, e->n_peers, e->skip, ++e->skip_gen, true, e->num_sms, e->stream);
   e->shared_epoch = e->volume_epoch;
   e->skip_epoch = 0;  // a local RayCast must look again: the map may describe more than this engine
+  SharedCache C{};
+  C.self = e->S.shard_rank;
+  if (e->cache) {
+    // content epoch: what was fetched stays valid until some shard integrates again (the caller knows: peers_unchanged)
+    if (!peers_unchanged) {
+      if (e->cache_epoch == 0x7FFFFFFF) { CU(cudaMemsetAsync(e->cache_stamp, 0, sizeof(int) * (size_t)e->n_peers * e->cache_stride, e->stream)); e->cache_epoch = 0; }
+      e->cache_epoch++;
+    }
+    e->cache_serial = (e->cache_serial + 1) & 0xFFFF;
+    C.cache = e->cache; C.stamp = e->cache_stamp; C.list = e->cache_list; C.count = e->cache_count;
+    C.stride = e->cache_stride; C.epoch = e->cache_epoch; C.serial = e->cache_serial; C.pad = e->cache_pad;
+  }
   launch_raycast_shared(e->d_peers, e->h_peers, e->n_peers, e->S.shard_shift, P, e->truncation / 2, e->skip, row0, std::min(rows, h - row0), tile_stride,
-                        e->S.n_mirror ? e->S.mirror[e->S.shard_rank] : nullptr, e->S.mirror_stride, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth, n_out, out_rgba, out_normal, out_depth, e->stream);
+                        e->S.n_mirror ? e->S.mirror[e->S.shard_rank] : nullptr, e->S.mirror_stride, C, (uchar4*)d_rgba, (uchar4*)d_normal, (float*)d_hit_depth,
+                        n_out, out_rgba, out_normal, out_depth, e->num_sms, e->stream);
   phase_end(e, PH_RAYCAST, e->stream);
   CU(cudaGetLastError());
   return TSDF_OK;
@@ -793,17 +817,79 @@ int tsdf_mirror_attach(tsdf_handle e, int world, void* const* mirrors, int strid
   return TSDF_OK;
 }
 
+static void free_shared_cache(tsdf_engine* e) {
+  cudaFree(e->cache); cudaFree(e->cache_stamp); cudaFree(e->cache_list); cudaFree(e->cache_count);
+  e->cache = nullptr; e->cache_stamp = nullptr; e->cache_list = nullptr; e->cache_count = nullptr; e->cache_stride = 0;
+}
+int tsdf_shared_cache_attach(tsdf_handle e, int stride_blocks, int pad_voxels) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  if (rc) return rc;
+  free_shared_cache(e);
+  if (stride_blocks == 0) return TSDF_OK;
+  if (e->n_peers < 2) return fail(TSDF_E_INVALID, "attach the peers first (tsdf_ipc_attach / tsdf_peer_attach_local), at least two shards");
+  if (stride_blocks < e->S.pool_blocks || stride_blocks >= (1 << kIndexShardShift)) return fail(TSDF_E_INVALID, "cache stride %d smaller than the pool (%d blocks)", stride_blocks, e->S.pool_blocks);
+  const size_t slots = (size_t)e->n_peers * stride_blocks;
+  CU(cudaMalloc(&e->cache, slots * kBlockVolume * sizeof(float)));
+  CU(cudaMalloc(&e->cache_stamp, slots * sizeof(int)));
+  CU(cudaMalloc(&e->cache_list, slots * sizeof(int)));
+  CU(cudaMalloc(&e->cache_count, 4 * sizeof(int)));
+  CU(cudaMemsetAsync(e->cache_stamp, 0, slots * sizeof(int), e->stream));
+  CU(cudaMemsetAsync(e->cache_count, 0, 4 * sizeof(int), e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->cache_stride = stride_blocks; e->cache_epoch = 1; e->cache_serial = 0; e->cache_pad = pad_voxels;
+  return TSDF_OK;
+}
+
+int tsdf_shared_cache_stats(tsdf_handle e, int64_t* blocks_fetched_last_view) {
+  if (!e || !blocks_fetched_last_view) return fail(TSDF_E_INVALID, "null argument");
+  *blocks_fetched_last_view = 0;
+  if (!e->cache) return TSDF_OK;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  int n = 0;
+  CU(cudaMemcpy(&n, e->cache_count + (e->cache_serial & 3), sizeof(int), cudaMemcpyDeviceToHost));
+  *blocks_fetched_last_view = n;
+  return TSDF_OK;
+}
+
+size_t tsdf_alloc_exchange_bytes(int world, int cap_keys) {
+  if (world < 1 || cap_keys < 1) return 0;
+  return (size_t)kXaHeaderBytes + 2 * (size_t)world * (size_t)cap_keys * sizeof(u64);
+}
+int tsdf_alloc_exchange_attach(tsdf_handle e, int world, void* const* inboxes, int cap_keys, tsdf_frame_hook hook, void* user) {
+  if (!e) return fail(TSDF_E_INVALID, "null engine handle");
+  CU(cudaSetDevice(e->device));
+  int rc = drain(e);
+  if (rc) return rc;
+  if (world == 0 || !inboxes) { e->S.xa_on = 0; e->xa_hook = nullptr; return TSDF_OK; }
+  if (world != e->S.shard_count || world > kMaxPeers || world < 2) return fail(TSDF_E_INVALID, "inbox count %d must equal shard_count %d (2..%d)", world, e->S.shard_count, kMaxPeers);
+  if (cap_keys < 1 || !hook) return fail(TSDF_E_INVALID, "cap_keys must be > 0 and the frame hook non-null");
+  for (int r = 0; r < world; ++r) if (!inboxes[r]) return fail(TSDF_E_INVALID, "null inbox pointer for rank %d", r);
+  if (!e->xa_cursor) CU(cudaMalloc(&e->xa_cursor, 16 * sizeof(int)));
+  CU(cudaMemsetAsync(e->xa_cursor, 0, 16 * sizeof(int), e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  for (int r = 0; r < world; ++r) e->S.xa_inbox[r] = (u64*)inboxes[r];
+  e->S.xa_cursor = e->xa_cursor; e->S.xa_cap = cap_keys; e->S.xa_parity = 0; e->xa_frames = 0;
+  e->xa_hook = hook; e->xa_user = user;
+  e->S.xa_on = 1;
+  return TSDF_OK;
+}
+
 int tsdf_raycast_shared(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
                         int row0, int rows, void* d_rgba, void* d_normal, void* d_hit_depth) {
   return raycast_shared_impl(e, max_depth, w, h, K, q, t, row0, rows, 1, false, d_rgba, d_normal, d_hit_depth, 0, nullptr, nullptr, nullptr);
 }
 int tsdf_raycast_shared_scatter(tsdf_handle e, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
-                                int tile_first, int tile_stride, int peers_unchanged, int n_dest, void* const* d_rgba,
+                                int tile_first, int tile_stride, int tile_count, int peers_unchanged, int n_dest, void* const* d_rgba,
                                 void* const* d_normal, void* const* d_hit_depth) {
   if (n_dest < 1) return fail(TSDF_E_INVALID, "need at least one destination");
-  if (tile_first < 0 || tile_stride < 1) return fail(TSDF_E_INVALID, "bad tile selection");
+  if (tile_first < 0 || tile_stride < 1 || tile_count < 0) return fail(TSDF_E_INVALID, "bad tile selection");
   if (tile_first * 8 >= h) return TSDF_OK;  // more ranks than tiles
-  return raycast_shared_impl(e, max_depth, w, h, K, q, t, tile_first * 8, h - tile_first * 8, tile_stride, peers_unchanged != 0, nullptr, nullptr,
+  int rows = h - tile_first * 8;  // the span of rows the launch may touch
+  if (tile_count > 0) rows = std::min<long long>(rows, ((long long)(tile_count - 1) * tile_stride + 1) * 8);
+  return raycast_shared_impl(e, max_depth, w, h, K, q, t, tile_first * 8, rows, tile_stride, peers_unchanged != 0, nullptr, nullptr,
                              nullptr, n_dest, d_rgba, d_normal, d_hit_depth);
 }
 

@@ -24,6 +24,46 @@ namespace tsdf {
 //      8-corner visibility test and the CAS insert.
 // ------------------------------------------------------------------------------------------
 constexpr int kInlineSteps = 4;
+
+// Candidate exchange (DeviceState::xa_on).  The candidates of a CTA (32 x 8 pixels, a few blocks) are collected in a small
+// shared-memory hash set first, so that every distinct block of the tile is mailed once: one cursor bump per owner and CTA
+// instead of one per warp and DDA step on a handful of hot words, and ~5x fewer keys for the owners to look up.
+constexpr int kXaSet = 256;  // slots of the per-CTA set (a tile whose rays meet more distinct blocks mails the rest directly)
+__device__ __forceinline__ void xa_mail_one(const DeviceState& S, u64 key, int owner, int pos) {
+  if (pos < S.xa_cap) {
+    u64* keys = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(S.xa_inbox[owner]) + kXaHeaderBytes);
+    keys[((size_t)(S.xa_parity * S.shard_count + S.shard_rank)) * S.xa_cap + pos] = key;  // local, or a posted store over NVLink
+  } else {
+    atomicOr(&S.ctr[C_ERROR], ERR_EXCHANGE);  // reported by this frame; the barrier kernel clamps the count it publishes
+  }
+}
+__device__ __forceinline__ void xa_collect(const DeviceState& S, u64* s_set, u64 key) {
+  unsigned h = (unsigned)hash_key(key) & (kXaSet - 1);
+  for (int probe = 0; probe < kXaSet; ++probe) {
+    const u64 prev = atomicCAS(reinterpret_cast<unsigned long long*>(s_set + h), (unsigned long long)kEmpty, (unsigned long long)key);
+    if (prev == kEmpty || prev == key) return;
+    h = (h + 1) & (kXaSet - 1);
+  }
+  const int owner = (int)owner_of(key, S.shard_count, S.shard_shift);  // set full
+  xa_mail_one(S, key, owner, atomicAdd(&S.xa_cursor[S.xa_parity * 8 + owner], 1));
+}
+// end of the CTA (all threads): mail the set
+__device__ __forceinline__ void xa_flush(const DeviceState& S, const u64* s_set, int* s_cnt, int* s_base) {
+  __syncthreads();
+  u64 key = kEmpty;
+  int owner = -1, pos = 0;
+  for (int t = threadIdx.x; t < kXaSet; t += blockDim.x) {  // (one slot per thread with 256 threads)
+    key = s_set[t];
+    if (key != kEmpty) { owner = (int)owner_of(key, S.shard_count, S.shard_shift); pos = atomicAdd(&s_cnt[owner], 1); }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < S.shard_count && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&S.xa_cursor[S.xa_parity * 8 + threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (key != kEmpty) xa_mail_one(S, key, owner, s_base[owner] + pos);
+}
+static_assert(kXaSet == 256, "xa_flush keeps one slot per thread of a 256-thread CTA");
+
+template <bool EXCHANGE>
 __global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, FrameParams P, FrameInput in,
                                                              Texel* __restrict__ tex) {
   const unsigned char* __restrict__ rgb = in.rgb;
@@ -62,6 +102,17 @@ __global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, F
     const uint32_t rgbx = (uint32_t)rgb[3 * idx] | ((uint32_t)rgb[3 * idx + 1] << 8) | ((uint32_t)rgb[3 * idx + 2] << 16);
     *reinterpret_cast<uint4*>(tex + idx) =
         make_uint4(__float_as_uint(valid ? d : 0.f), __float_as_uint(range), __float_as_uint(dlogit), rgbx);
+  }
+  // candidate exchange: the staging above is needed on every rank (the integrate kernel gathers from it), the ray walk
+  // below only on the rank this 32 x 8 tile is dealt to
+  constexpr bool exchange = EXCHANGE;
+  if (exchange && (blockIdx.y * gridDim.x + blockIdx.x) % (unsigned)S.shard_count != (unsigned)S.shard_rank) return;
+  __shared__ u64 s_set[EXCHANGE ? kXaSet : 1];
+  __shared__ int s_cnt[8], s_base[8];
+  if (exchange) {
+    s_set[threadIdx.x] = kEmpty;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
   }
 
   // ---- ray set-up, utils/tsdf/voxel_tsdf.cu:124-139 (divisions share one reciprocal per divisor, see div_by) ----
@@ -122,7 +173,11 @@ __global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, F
         // warp-cooperative de-duplication: one lane per distinct block coordinate probes the table
         const unsigned peers = __match_any_sync(0xFFFFFFFFu, key[i]);
         lead[i] = (key[i] != kEmpty) && ((unsigned)(__ffs(peers) - 1) == lane) &&
-                  (!sharded || owner_of(key[i], S.shard_count, S.shard_shift) == (unsigned)S.shard_rank);
+                  (exchange || !sharded || owner_of(key[i], S.shard_count, S.shard_shift) == (unsigned)S.shard_rank);
+        if (exchange) {  // the owner looks the key up after the barrier
+          if (lead[i]) { xa_collect(S, s_set, key[i]); ++n_cand; }
+          lead[i] = false;
+        }
         // L1-cached look at the home slot: a key seen here IS present (keys only appear during this kernel, and L1
         // does not outlive a kernel); anything else is settled by the coherent probe below
         if (lead[i]) first[i] = ld_key_ca(S.table + (hash_key(key[i]) & S.table_mask));
@@ -160,6 +215,10 @@ __global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, F
       }
       const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
       const bool leader = (key != kEmpty) && ((unsigned)(__ffs(peers) - 1) == lane);
+      if (exchange) {
+        if (leader) { xa_collect(S, s_set, key); ++n_cand; }
+        continue;
+      }
       if (leader && (!sharded || owner_of(key, S.shard_count, S.shard_shift) == (unsigned)S.shard_rank)) {
         ++n_cand;
         if (!table_contains(S, key)) {
@@ -169,6 +228,7 @@ __global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, F
       }
     }
   }
+  if (exchange) xa_flush(S, s_set, s_cnt, s_base);
   // counters: one atomic per warp
   n_cand = __reduce_add_sync(0xFFFFFFFFu, n_cand);
   n_new = __reduce_add_sync(0xFFFFFFFFu, n_new);
@@ -176,6 +236,42 @@ __global__ void __launch_bounds__(256, 6) frame_allocate_kernel(DeviceState S, F
     if (n_cand) atomicAdd(&S.ctr[C_NCAND], n_cand);
     if (n_new) atomicAdd(&S.ctr[C_NNEW], n_new);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// insert_candidates_kernel: the owner's half of the candidate exchange.  blockIdx.y = sending rank; its keys for this
+// frame sit in this rank's inbox (complete and visible: a barrier over the ranks lies between the senders' allocate
+// kernels and this launch).  Same rule as above: a present block is left alone, an absent one is inserted if all eight
+// corners project into the image (voxel_tsdf.cu:144) -- tested by eight lanes at once.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) insert_candidates_kernel(DeviceState S, FrameParams P) {
+  const unsigned lane = threadIdx.x & 31;
+  const int src = blockIdx.y;
+  const unsigned char* inbox = reinterpret_cast<const unsigned char*>(S.xa_inbox[S.shard_rank]);
+  const int n = min(reinterpret_cast<const int*>(inbox)[S.xa_parity * 8 + src], S.xa_cap);
+  const u64* keys = reinterpret_cast<const u64*>(inbox + kXaHeaderBytes) + (size_t)(S.xa_parity * S.shard_count + src) * S.xa_cap;
+  int n_new = 0;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + (int)lane;
+    u64 key = kEmpty;
+    bool absent = false;
+    if (i < n) { key = keys[i]; absent = !table_contains(S, key); }
+    for (unsigned todo = __ballot_sync(0xFFFFFFFFu, absent); todo; todo &= todo - 1) {
+      const int from = __ffs(todo) - 1;
+      const u64 k = __shfl_sync(0xFFFFFFFFu, key, from);
+      int bx, by, bz; unpack_key(k, bx, by, bz);
+      const int cx = (short)((short)(bx << 3) + ((lane >> 0) & 1) * (kBlockLen - 1));
+      const int cy = (short)((short)(by << 3) + ((lane >> 1) & 1) * (kBlockLen - 1));
+      const int cz = (short)((short)(bz << 3) + ((lane >> 2) & 1) * (kBlockLen - 1));
+      const unsigned vis = __ballot_sync(0xFFFFFFFFu, voxel_visible(cx, cy, cz, P));
+      if ((vis & 0xFFu) == 0xFFu && (int)lane == from && table_insert(S, k) == 1) ++n_new;
+    }
+  }
+  n_new = __reduce_add_sync(0xFFFFFFFFu, n_new);
+  if (lane == 0 && n_new) atomicAdd(&S.ctr[C_NNEW], n_new);
+  // this frame's cursors have been published (by the barrier kernel, earlier on this stream): clear them for the frame
+  // after next, which uses this half again
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8) S.xa_cursor[S.xa_parity * 8 + threadIdx.x] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -462,7 +558,12 @@ __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kerne
 // launchers
 // ------------------------------------------------------------------------------------------
 void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const FrameInput& in, Texel* tex, cudaStream_t st) {
-  frame_allocate_kernel<<<dim3((P.w + 31) / 32, (P.h + 7) / 8), 256, 0, st>>>(S, P, in, tex);
+  const dim3 grid((P.w + 31) / 32, (P.h + 7) / 8);
+  if (S.xa_on) frame_allocate_kernel<true><<<grid, 256, 0, st>>>(S, P, in, tex);
+  else frame_allocate_kernel<false><<<grid, 256, 0, st>>>(S, P, in, tex);
+}
+void launch_insert_candidates(const DeviceState& S, const FrameParams& P, cudaStream_t st) {
+  insert_candidates_kernel<<<dim3(32, S.shard_count), 256, 0, st>>>(S, P);
 }
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int* vis_state, int num_sms, cudaStream_t st) {
   select_visible_kernel<<<num_sms * 4, 256, 0, st>>>(S, P, visible, vis_state);

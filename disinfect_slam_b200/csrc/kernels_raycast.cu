@@ -152,7 +152,7 @@ struct BlockCache { int bx, by, bz; int entry; };  // bx = INT_MIN: nothing cach
 
 // Where the voxels of a block live.  A block is named by its ENTRY: the pool index (local volume), or owner shard
 // << kIndexShardShift | pool index (sharded volume) -- exactly what the map's occupied cells hold.
-//   tsdf(entry)   the block's TSDF plane, all the march and the gradient need
+//   tsdf_at(entry, voxel)   a value of the block's TSDF plane, all the march and the gradient need
 //   block(entry)  the block itself, for the colour / logit of the one hit voxel
 // Local: this engine's table and pool.  Shared: the pool of the shard that owns the block, reached through peer-mapped
 // pointers (NVLink loads inside the march) -- or, when the shards keep TSDF mirrors, a LOCAL copy of every shard's
@@ -161,13 +161,19 @@ template <bool SHARED> struct Volume;
 template <> struct Volume<false> {
   DeviceState S;
   __device__ __forceinline__ const unsigned char* block(int entry) const { return S.voxels + (size_t)entry * kBlockBytes; }
-  __device__ __forceinline__ const float* tsdf(int entry) const { return reinterpret_cast<const float*>(block(entry)); }
+  __device__ __forceinline__ float tsdf_at(int entry, int voxel) const { return __ldg(reinterpret_cast<const float*>(block(entry)) + voxel); }
   __device__ __forceinline__ int find_entry(int bx, int by, int bz) const { return table_find(S, pack_key(bx, by, bz)); }
 };
 template <> struct Volume<true> {
   const PeerView* shards; int n_shards, shard_shift;
   const unsigned char* pool[kMaxPeers];    // every shard's voxel pool (peer-mapped): kernel parameters, not a load per sample
   const float* mirror; int mirror_stride;  // local TSDF mirror of all shards ([shard][pool index][512]) or null
+  // Pulled TSDF cache (tsdf_shared_cache_attach): like the mirror a local [shard][pool index][512] array, but filled on
+  // demand -- before the march, pull_select / pull_copy_kernel fetch the TSDF planes of the foreign blocks that can meet
+  // this launch's rays (bulk NVLink reads, all in flight together) and stamp them with the current content epoch.  A
+  // sample of a foreign block whose stamp is not current falls back to the owner's memory, so the result never depends
+  // on how good the frustum test was.  Own blocks are read from the own pool.
+  const float* cache; const int* cache_stamp; int cache_epoch, self;
   // Fused exchange of the results: when n_out > 0 every ray's pixel is stored into the image buffers of ALL ranks
   // (peer-mapped pointers, posted stores over NVLink issued as the rays finish) instead of into one local image that an
   // all-gather would have to distribute afterwards.
@@ -178,9 +184,17 @@ template <> struct Volume<true> {
   __device__ __forceinline__ const unsigned char* block(int entry) const {  // owner shard in the top bits: no table probe over NVLink
     return pool[entry >> kIndexShardShift] + (size_t)(entry & ((1 << kIndexShardShift) - 1)) * kBlockBytes;
   }
-  __device__ __forceinline__ const float* tsdf(int entry) const {
-    if (mirror) return mirror + ((size_t)(entry >> kIndexShardShift) * mirror_stride + (entry & ((1 << kIndexShardShift) - 1))) * kBlockVolume;
-    return reinterpret_cast<const float*>(block(entry));
+  __device__ __forceinline__ float tsdf_at(int entry, int voxel) const {
+    const int shard = entry >> kIndexShardShift, idx = entry & ((1 << kIndexShardShift) - 1);
+    if (mirror) return __ldg(mirror + ((size_t)shard * mirror_stride + idx) * kBlockVolume + voxel);
+    const float* home = reinterpret_cast<const float*>(pool[shard] + (size_t)idx * kBlockBytes) + voxel;
+    if (cache && shard != self) {
+      const size_t slot = (size_t)shard * mirror_stride + idx;
+      const int stamp = __ldg(cache_stamp + slot);         // both loads are local and in flight together
+      const float v = __ldg(cache + slot * kBlockVolume + voxel);
+      if (stamp == cache_epoch) return v;
+    }
+    return __ldg(home);
   }
   __device__ __forceinline__ int find_entry(int bx, int by, int bz) const {
     const u64 key = pack_key(bx, by, bz);
@@ -246,7 +260,7 @@ template <class V>
 __device__ __forceinline__ float fetch_tsdf(const V& vol, const Grid& G, BlockCache& c, int px, int py, int pz) {
   cache_lookup(vol, G, c, px, py, pz);
   if (c.entry < 0) return 1.f;
-  return __ldg(vol.tsdf(c.entry) + voxel_index(px, py, pz));
+  return vol.tsdf_at(c.entry, voxel_index(px, py, pz));
 }
 template <bool CLAMP, class V>
 __device__ __forceinline__ float fetch_tsdf_f(const V& vol, const Grid& G, BlockCache& c, float3 p) {
@@ -269,7 +283,7 @@ __device__ __forceinline__ float march_sample(const V& vol, const Grid& G, float
   float t = 1.f;
   if (g >= 0) {
     const int entry = DENSE ? g : vol.find_entry(bx, by, bz);
-    if (DENSE || entry >= 0) t = __ldg(vol.tsdf(entry) + voxel_index(px, py, pz));
+    if (DENSE || entry >= 0) t = vol.tsdf_at(entry, voxel_index(px, py, pz));
   } else if (g == kEscaped) {
     skip = kEscaped;  // the ray has left the volume for good
   } else if (g <= -2) {
@@ -311,6 +325,81 @@ __device__ __forceinline__ bool march(const V& vol, const Grid& G, f32x2& pxy, f
     }
     i += k + 1;
     if (i >= max_step) return false;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pulled TSDF cache of a sharded volume (see Volume<true>)
+// ------------------------------------------------------------------------------------------
+// The rays of a launch lie in the pyramid { x/z in [xlo, xhi], y/z in [ylo, yhi], 0 <= z <= zfar } of the camera frame.
+// A block whose (padded) box has all eight corners beyond one of the six planes cannot contain a sample of these rays;
+// every other foreign block that is not in the cache at the current content epoch is listed.  The padding covers the
+// nearest-voxel rounding, the +-1 voxel gradient samples and the float32 accumulation of the positions; a block the test
+// wrongly drops is read from its owner sample by sample (tsdf_at), so the image cannot change (`pad` voxels; 3 covers all
+// of that with room to spare, a negative value makes the test drop blocks and is what the tests use to walk the fallback).
+struct PullView { float xlo, xhi, ylo, yhi, zfar; };
+__global__ void __launch_bounds__(256) pull_select_kernel(const PeerView* __restrict__ shards, int n_shards, int self, FrameParams P, PullView F,
+                                                          const int* __restrict__ stamp, int stride, int epoch, int pad, int* __restrict__ list,
+                                                          int* __restrict__ count, int serial) {
+  const unsigned lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) count[(serial + 1) & 3] = 0;  // the next launch's counter (nobody touches it now)
+  int* const n_listed = count + (serial & 3);
+  for (int r = 0; r < n_shards; ++r) {
+    if (r == self) continue;
+    const int hw = shards[r].ctr[C_HIGH_WATER];
+    const u64* dir = shards[r].block_key;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < hw; base += gridDim.x * blockDim.x) {
+      const int i = base + (int)lane;
+      bool want = false;
+      if (i < hw && i < stride) {
+        const u64 k = dir[i];
+        if (k != kEmpty && stamp[(size_t)r * stride + i] != epoch) {
+          int bx, by, bz; unpack_key(k, bx, by, bz);
+          unsigned beyond = 0x3Fu;  // bit p: every corner so far lies beyond plane p
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float wx = (float)((bx << 3) + ((c & 1) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
+            const float wy = (float)((by << 3) + ((c & 2) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
+            const float wz = (float)((bz << 3) + ((c & 4) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
+            const float3 q = apply(P.cam_T_world, f3(wx, wy, wz));
+            unsigned in = 0u;
+            if (!(q.x - F.xlo * q.z < 0.f)) in |= 1u;
+            if (!(q.x - F.xhi * q.z > 0.f)) in |= 2u;
+            if (!(q.y - F.ylo * q.z < 0.f)) in |= 4u;
+            if (!(q.y - F.yhi * q.z > 0.f)) in |= 8u;
+            if (!(q.z < 0.f)) in |= 16u;
+            if (!(q.z > F.zfar)) in |= 32u;
+            beyond &= ~in;
+          }
+          want = beyond == 0u;
+        }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+      if (m) {
+        int off = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) off = atomicAdd(n_listed, __popc(m));
+        off = __shfl_sync(0xFFFFFFFFu, off, __ffs(m) - 1);
+        if (want) list[off + __popc(m & ((1u << lane) - 1u))] = (r << kIndexShardShift) | i;
+      }
+    }
+  }
+}
+// one warp per listed block: its 2 KB TSDF plane in four 16-byte loads per lane, all issued before the first store
+struct PullPools { const unsigned char* pool[kMaxPeers]; };
+__global__ void __launch_bounds__(256) pull_copy_kernel(PullPools pools, const int* __restrict__ list, const int* __restrict__ count, int serial,
+                                                        float* __restrict__ cache, int* __restrict__ stamp, int stride, int epoch) {
+  const int n = count[serial & 3];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n; b += warps) {
+    const int entry = list[b];
+    const int shard = entry >> kIndexShardShift, idx = entry & ((1 << kIndexShardShift) - 1);
+    const float4* src = reinterpret_cast<const float4*>(pools.pool[shard] + (size_t)idx * kBlockBytes);
+    const size_t slot = (size_t)shard * stride + idx;
+    float4* dst = reinterpret_cast<float4*>(cache + slot * kBlockVolume);
+    const float4 v0 = __ldcg(src + lane), v1 = __ldcg(src + lane + 32), v2 = __ldcg(src + lane + 64), v3 = __ldcg(src + lane + 96);
+    dst[lane] = v0; dst[lane + 32] = v1; dst[lane + 64] = v2; dst[lane + 96] = v3;
+    if (lane == 0) stamp[slot] = epoch;
   }
 }
 
@@ -422,7 +511,7 @@ __global__ void __launch_bounds__(256) raycast_kernel(Volume<SHARED> vol, FrameP
     }
     float gv[6];
 #pragma unroll
-    for (int n = 0; n < 6; ++n) gv[n] = nentry[n] >= 0 ? __ldg(vol.tsdf(nentry[n]) + voxel_index(nx[n], ny[n], nz[n])) : 1.f;
+    for (int n = 0; n < 6; ++n) gv[n] = nentry[n] >= 0 ? vol.tsdf_at(nentry[n], voxel_index(nx[n], ny[n], nz[n])) : 1.f;
     const float prob = centry >= 0 ? logit_to_prob(lgt) : 0.f;
     const float gxp = gv[0], gxn = gv[1], gyp = gv[2], gyn = gv[3], gzp = gv[4], gzn = gv[5];
     const float3 nrm = f3(gxp - gxn, gyp - gyn, gzp - gzn);
@@ -494,9 +583,9 @@ void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size,
 // mapped in `shards` (device array): bit-identical to the single-volume render, voxels of foreign blocks are read
 // from their owner over NVLink.
 void launch_raycast_shared(const PeerView* shards, const PeerView* host_shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
-                           const SkipMap& M, int row0, int rows, int tile_stride, const float* mirror, int mirror_stride, uchar4* rgba,
-                           uchar4* normal, float* hit_depth, int n_out, void* const* out_rgba, void* const* out_normal,
-                           void* const* out_depth, cudaStream_t st) {
+                           const SkipMap& M, int row0, int rows, int tile_stride, const float* mirror, int mirror_stride, const SharedCache& C,
+                           uchar4* rgba, uchar4* normal, float* hit_depth, int n_out, void* const* out_rgba, void* const* out_normal,
+                           void* const* out_depth, int num_sms, cudaStream_t st) {
   if (rows <= 0) return;
   // tile_stride > 1: `rows` bounds the rows of the image this launch may touch ([row0, row0 + rows)), of which it
   // renders every tile_stride-th 8-row tile starting at row0
@@ -507,7 +596,21 @@ void launch_raycast_shared(const PeerView* shards, const PeerView* host_shards, 
   vol.n_out = n_out;
   vol.tile_stride = tile_stride;
   vol.mirror = mirror; vol.mirror_stride = mirror_stride;
+  vol.cache = nullptr; vol.cache_stamp = nullptr; vol.cache_epoch = 0; vol.self = C.self;
   for (int r = 0; r < kMaxPeers; ++r) vol.pool[r] = r < n_shards ? host_shards[r].voxels : nullptr;
+  if (!mirror && C.cache && n_shards > 1) {
+    // fetch what the rays of rows [row0, row0 + rows) can meet (one pixel of slack on every side of the band)
+    const float xa = P.Kinv.fx * -1.f + P.Kinv.cx, xb = P.Kinv.fx * (float)P.w + P.Kinv.cx;
+    const float ya = P.Kinv.fy * (float)(row0 - 1) + P.Kinv.cy, yb = P.Kinv.fy * (float)(row0 + rows) + P.Kinv.cy;
+    PullView F;
+    F.xlo = fminf(xa, xb); F.xhi = fmaxf(xa, xb); F.ylo = fminf(ya, yb); F.yhi = fmaxf(ya, yb);
+    F.zfar = P.max_depth + 2.f * step_size;
+    PullPools pools;
+    for (int r = 0; r < kMaxPeers; ++r) pools.pool[r] = vol.pool[r];
+    pull_select_kernel<<<num_sms * 2, 256, 0, st>>>(shards, n_shards, C.self, P, F, C.stamp, C.stride, C.epoch, C.pad, C.list, C.count, C.serial);
+    pull_copy_kernel<<<num_sms * 8, 256, 0, st>>>(pools, C.list, C.count, C.serial, C.cache, C.stamp, C.stride, C.epoch);
+    vol.cache = C.cache; vol.cache_stamp = C.stamp; vol.cache_epoch = C.epoch; vol.mirror_stride = C.stride;
+  }
   for (int r = 0; r < kMaxPeers; ++r) {
     vol.out_rgba[r] = r < n_out && out_rgba ? (uchar4*)out_rgba[r] : nullptr;
     vol.out_normal[r] = r < n_out && out_normal ? (uchar4*)out_normal[r] : nullptr;

@@ -55,7 +55,7 @@ constexpr int kMaxRanks = 8;
 constexpr size_t kFlagBytes = 256;
 constexpr size_t kRowSlack = (size_t)kMaxRanks * 8192;  // pixels: the in-place all-gather pads the image to world * rows_per rows
 constexpr int kStage = 3;  // frame staging sets: broadcast of frame k+1 while frame k integrates and k-1 retires
-enum { T_BCAST = 0, T_BARRIER, T_ALLGATHER, T_COMPOSITE, T_RAYCAST, T_GATHER, T_COUNT };
+enum { T_BCAST = 0, T_BARRIER, T_ALLGATHER, T_COMPOSITE, T_RAYCAST, T_GATHER, T_XBARRIER, T_COUNT };
 
 struct Stage {
   unsigned char* buf = nullptr;     // [depth f32 | ht f32 | lt f32 | rgb u8 x 3] x max_image_pixels
@@ -87,6 +87,11 @@ struct tsdf_mgpu {
   // TSDF mirror of this rank: every shard's TSDF planes, kept up to date by the owners' integrate kernels (tsdf_mirror_attach)
   float* mirror = nullptr;
   void* mopened[kMaxRanks] = {};
+  int mirror_mode = 0;                      // 0 none (foreign voxels over NVLink sample by sample), 1 pushed mirrors, 2 pulled cache
+  bool row_bands = false;                   // one contiguous band of rows per rank instead of 8-row tiles dealt round-robin
+  // candidate exchange (tsdf_alloc_exchange_attach): this rank's inbox, every rank's as seen from here, keys per sender
+  unsigned char* inbox = nullptr; unsigned char* ipeer[kMaxRanks] = {}; void* iopened[kMaxRanks] = {}; int xa_cap = 0;
+  bool pending_barrier = false;             // run_sequence: the barrier after a view is supplied by the next frame's exchange barrier
   int last_w = 0, last_h = 0;
   unsigned long long* keys = nullptr; size_t keys_cap = 0;
   long long* d_sizes = nullptr; long long* h_sizes = nullptr;  // [world] gather sizes / counter sums
@@ -130,9 +135,13 @@ int rows_per_rank(const tsdf_mgpu* m, int h) { return (h + m->world - 1) / m->wo
 // stream wrote -- voxels, image rows stored into peer buffers -- is visible to whoever acquires the flag), then waits
 // until peer r's arrival shows up in the own flag word [r].  Epochs only grow, a fast peer may already be one ahead.
 struct PeerFlags { int* flags[kMaxRanks]; };
-__global__ void peer_barrier_kernel(PeerFlags peers, int rank, int world, int epoch, long long timeout_cycles, int* err) {
+// Optional mail run of the candidate exchange: before signalling, lane r tells peer r how many keys this rank has put into
+// its inbox for the frame of this parity (count word [parity * 8 + rank] of r's inbox header).
+struct PeerCounts { const int* cursor; int* header[kMaxRanks]; int slot, cap; };
+__global__ void peer_barrier_kernel(PeerFlags peers, PeerCounts mail, int rank, int world, int epoch, long long timeout_cycles, int* err) {
   const int r = threadIdx.x;
   if (r >= world) return;
+  if (mail.cursor) mail.header[r][mail.slot] = min(mail.cursor[r], mail.cap);
   __threadfence_system();
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.flags[r] + rank), "r"(epoch) : "memory");
   const int* mine = peers.flags[rank] + r;
@@ -145,7 +154,7 @@ __global__ void peer_barrier_kernel(PeerFlags peers, int rank, int world, int ep
   }
 }
 
-struct XBlob { cudaIpcMemHandle_t h; cudaIpcMemHandle_t hm; long long pid; void* raw; void* raw_mirror; int device; int pool_blocks; };
+struct XBlob { cudaIpcMemHandle_t h; cudaIpcMemHandle_t hm; cudaIpcMemHandle_t hi; long long pid; void* raw; void* raw_mirror; void* raw_inbox; int device; int pool_blocks; };
 }  // namespace
 
 extern "C" {
@@ -175,7 +184,9 @@ int tsdf_mgpu_destroy(tsdf_mgpu_handle m) {
   }
   for (int r = 0; r < kMaxRanks; ++r) if (m->xopened[r]) cudaIpcCloseMemHandle(m->xopened[r]);
   for (int r = 0; r < kMaxRanks; ++r) if (m->mopened[r]) cudaIpcCloseMemHandle(m->mopened[r]);
-  cudaFree(m->xbuf); cudaFree(m->d_err); cudaFree(m->mirror);
+  for (int r = 0; r < kMaxRanks; ++r) if (m->iopened[r]) cudaIpcCloseMemHandle(m->iopened[r]);
+  if (m->eng) tsdf_alloc_exchange_attach(m->eng, 0, nullptr, 0, nullptr, nullptr);  // (drains the engine)
+  cudaFree(m->xbuf); cudaFree(m->d_err); cudaFree(m->mirror); cudaFree(m->inbox);
   cudaFree(m->d_flag); cudaFree(m->keys); cudaFree(m->d_sizes); cudaFree(m->gather_all);
   if (m->h_sizes) cudaFreeHost(m->h_sizes);
   collect(m);
@@ -185,6 +196,8 @@ int tsdf_mgpu_destroy(tsdf_mgpu_handle m) {
   delete m;
   return TSDF_OK;
 }
+
+static void xa_frame_hook(void* user, void* stream, const int* d_cursor, int parity);
 
 int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user_cfg, int rank, int world, const void* id,
                      tsdf_mgpu_handle* out) {
@@ -253,8 +266,22 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
     {
       const char* ex = getenv("TSDF_MGPU_EXCHANGE");
       m->fused = !(ex && !strcmp(ex, "nccl"));
+      // How the march gets at foreign TSDF samples.  Default: pulled cache (before the march every rank fetches the TSDF
+      // planes of the foreign blocks its rays can meet: about a room's worth, a few MB).  TSDF_MGPU_MIRROR=push: mirrors
+      // written by the owners' integrate kernels (every rank receives every update of every frame: NVLink-ingress bound
+      // beyond 2 GPUs); =0: neither, every foreign sample is a load over NVLink.  The NCCL-exchange variant keeps the
+      // plain form.
       const char* mi = getenv("TSDF_MGPU_MIRROR");
-      const bool want_mirror = world > 1 && !(mi && !strcmp(mi, "0"));
+      m->mirror_mode = world < 2 ? 0 : (mi && !strcmp(mi, "0")) ? 0 : (mi && !strcmp(mi, "push")) ? 1 : (mi && !strcmp(mi, "pull")) ? 2 : (m->fused ? 2 : 0);
+      const bool want_mirror = m->mirror_mode == 1;
+      // Which rows a rank renders: 8-row tiles dealt round-robin (default: every rank gets the same mix of cheap and
+      // expensive rows) or TSDF_MGPU_TILES=band, one contiguous band per rank (fewer foreign blocks to fetch, but the
+      // ranks finish at different times)
+      const char* ti = getenv("TSDF_MGPU_TILES");
+      m->row_bands = ti && !strcmp(ti, "band");
+      // Candidate exchange (allocation pass sharded by image tiles): needs the peer barrier, i.e. the fused plane
+      const char* al = getenv("TSDF_MGPU_ALLOC");
+      const bool want_exchange = world > 1 && m->fused && !(al && !strcmp(al, "owner"));
       std::vector<XBlob> xb(world);
       XBlob mine{};
       CU(cudaIpcGetMemHandle(&mine.h, m->xbuf));
@@ -265,6 +292,16 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
         CU(cudaMemsetAsync(m->mirror, 0, bytes, m->es));
         CU(cudaIpcGetMemHandle(&mine.hm, m->mirror));
         mine.raw_mirror = m->mirror;
+      }
+      if (want_exchange) {
+        // a sender walks 1/world of the pixels; four keys per pixel covers every frame whose rays stay within the inline
+        // DDA length, with room to spare (typical frames mail ~0.1 key per pixel after the warp-level de-duplication)
+        m->xa_cap = (int)std::max<size_t>(65536, 4 * ((m->max_px + world - 1) / world));
+        const size_t bytes = tsdf_alloc_exchange_bytes(world, m->xa_cap);
+        CU(cudaMalloc(&m->inbox, bytes));
+        CU(cudaMemsetAsync(m->inbox, 0, bytes, m->es));
+        CU(cudaIpcGetMemHandle(&mine.hi, m->inbox));
+        mine.raw_inbox = m->inbox;
       }
       XBlob* d_xb = nullptr;
       CU(cudaMalloc(&d_xb, sizeof(XBlob) * world));
@@ -297,6 +334,21 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
           else { CU(cudaIpcOpenMemHandle(&mp[r], xb[r].hm, cudaIpcMemLazyEnablePeerAccess)); m->mopened[r] = mp[r]; }
         }
         TS(tsdf_mirror_attach(m->eng, world, mp, cfg.pool_blocks));
+      }
+      if (m->mirror_mode == 2) {
+        for (int r = 0; r < world; ++r)
+          if (xb[r].pool_blocks != cfg.pool_blocks) return fail(TSDF_E_INVALID, "the TSDF cache needs the same pool_blocks on every rank (%d vs %d)", xb[r].pool_blocks, cfg.pool_blocks);
+        TS(tsdf_shared_cache_attach(m->eng, cfg.pool_blocks, 3));
+      }
+      if (want_exchange) {
+        void* ip[kMaxRanks] = {};
+        for (int r = 0; r < world; ++r) {
+          if (r == rank) ip[r] = m->inbox;
+          else if (xb[r].pid == (long long)getpid()) ip[r] = xb[r].raw_inbox;
+          else { CU(cudaIpcOpenMemHandle(&ip[r], xb[r].hi, cudaIpcMemLazyEnablePeerAccess)); m->iopened[r] = ip[r]; }
+          m->ipeer[r] = (unsigned char*)ip[r];
+        }
+        TS(tsdf_alloc_exchange_attach(m->eng, world, ip, m->xa_cap, xa_frame_hook, m));
       }
       // nobody may signal into a buffer that its owner is still clearing
       NC(ncclAllReduce(m->d_flag, m->d_flag, 1, ncclInt, ncclSum, m->comm_sync, m->es));
@@ -368,17 +420,42 @@ static int ensure_images(tsdf_mgpu* m, int w, int h) {
   return TSDF_OK;
 }
 
-static int peer_barrier(tsdf_mgpu* m) {
+static int peer_barrier(tsdf_mgpu* m, const int* d_cursor = nullptr, int parity = 0) {
   PeerFlags pf{};
   for (int r = 0; r < m->world; ++r) pf.flags[r] = reinterpret_cast<int*>(m->xpeer[r] + 3 * m->img_stride);
+  PeerCounts mail{};
+  if (d_cursor) {
+    mail.cursor = d_cursor; mail.slot = parity * 8 + m->rank; mail.cap = m->xa_cap;
+    for (int r = 0; r < m->world; ++r) mail.header[r] = reinterpret_cast<int*>(m->ipeer[r]);
+  }
   m->epoch++;
-  peer_barrier_kernel<<<1, 32, 0, m->es>>>(pf, m->rank, m->world, m->epoch, 4000000000ll, m->d_err);  // ~2 s
+  m->pending_barrier = false;  // whatever an earlier view left open, this barrier closes
+  peer_barrier_kernel<<<1, 32, 0, m->es>>>(pf, mail, m->rank, m->world, m->epoch, 4000000000ll, m->d_err);  // ~2 s
   CU(cudaGetLastError());
   return TSDF_OK;
 }
+// The engine calls this between a frame's allocate kernel and the owner's inserts (candidate exchange): publish how many
+// keys went to every peer, and order the ranks.  It also stands in for the barrier a preceding view left open.
+static void xa_frame_hook(void* user, void* /*stream: the engine's, == m->es*/, const int* d_cursor, int parity) {
+  tsdf_mgpu* m = static_cast<tsdf_mgpu*>(user);
+  Timed tm(m, T_XBARRIER, m->es);
+  peer_barrier(m, d_cursor, parity);
+}
+static int flush_barrier(tsdf_mgpu* m) {
+  if (!m->pending_barrier) return TSDF_OK;
+  Timed tm(m, T_ALLGATHER, m->es);
+  return peer_barrier(m);
+}
 
+static int raycast_impl(tsdf_mgpu_handle m, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                        const void** d_rgba, const void** d_normal, const void** d_depth, bool defer_barrier);
 int tsdf_mgpu_raycast(tsdf_mgpu_handle m, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
                       const void** d_rgba, const void** d_normal, const void** d_depth) {
+  return raycast_impl(m, max_depth, w, h, K, q, t, d_rgba, d_normal, d_depth, false);
+}
+
+static int raycast_impl(tsdf_mgpu_handle m, float max_depth, int w, int h, const float K[4], const float q[4], const float t[3],
+                        const void** d_rgba, const void** d_normal, const void** d_depth, bool defer_barrier) {
   if (!m || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
   if (w <= 0 || h <= 0) return fail(TSDF_E_INVALID, "bad image size %dx%d", w, h);
   CU(cudaSetDevice(m->device));
@@ -394,11 +471,21 @@ int tsdf_mgpu_raycast(tsdf_mgpu_handle m, float max_depth, int w, int h, const f
       Timed tm(m, T_RAYCAST, m->es);
       void* o[3][kMaxRanks];
       for (int i = 0; i < 3; ++i) for (int r = 0; r < m->world; ++r) o[i][r] = m->xpeer[r] + (size_t)i * m->img_stride;
-      // 8-row tiles dealt out round-robin: every rank renders the same mix of rows
-      TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, m->rank, m->world, m->views_since_integrate > 0 ? 1 : 0, m->world, o[0], o[1], o[2]));
+      const int unchanged = m->views_since_integrate > 0 ? 1 : 0;
+      if (m->row_bands) {
+        const int tiles = (h + 7) / 8, per = (tiles + m->world - 1) / m->world;
+        TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, m->rank * per, 1, per, unchanged, m->world, o[0], o[1], o[2]));
+      } else {
+        // 8-row tiles dealt out round-robin: every rank renders the same mix of rows
+        TS(tsdf_raycast_shared_scatter(m->eng, max_depth, w, h, K, q, t, m->rank, m->world, 0, unchanged, m->world, o[0], o[1], o[2]));
+      }
       m->views_since_integrate++;
     }
-    { Timed tm(m, T_ALLGATHER, m->es); int rc2 = peer_barrier(m); if (rc2) return rc2; }
+    // barrier after the march: all rows have arrived everywhere, every peer is done with this rank's voxels.  Inside
+    // tsdf_mgpu_run_sequence the next frame's exchange barrier does that job (nothing before it touches the volume or
+    // the images), so the view costs one barrier less
+    if (defer_barrier && m->inbox) m->pending_barrier = true;
+    else { Timed tm(m, T_ALLGATHER, m->es); int rc2 = peer_barrier(m); if (rc2) return rc2; }
   } else {
     if (m->world > 1) {  // every shard's Integrate has finished before any rank reads its voxels
       Timed tm(m, T_BARRIER, m->es);
@@ -428,6 +515,7 @@ int tsdf_mgpu_raycast_composite(tsdf_mgpu_handle m, float max_depth, int w, int 
   if (!m || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
   if (w <= 0 || h <= 0) return fail(TSDF_E_INVALID, "bad image size %dx%d", w, h);
   CU(cudaSetDevice(m->device));
+  { int rcb = flush_barrier(m); if (rcb) return rcb; }
   const size_t need = 2 * (size_t)w * h;
   if (need > m->keys_cap) {
     CU(cudaStreamSynchronize(m->es));
@@ -548,10 +636,11 @@ int tsdf_mgpu_run_sequence(tsdf_mgpu_handle m, int root, int on_device, const ts
     int rc = tsdf_mgpu_integrate(m, root, on_device, f.rgb, f.depth, f.ht, f.lt, w, h, max_depth, K, f.q_xyzw, f.t_xyz);
     if (rc == TSDF_E_POOL_EXHAUSTED || rc == TSDF_E_TABLE_FULL) { deferred = rc; rc = TSDF_OK; }  // reported at the end; the stream goes on
     if (rc) return rc;
-    if (raycast_mode == 1) rc = tsdf_mgpu_raycast(m, max_depth, w, h, K, f.q_xyzw, f.t_xyz, nullptr, nullptr, nullptr);
+    if (raycast_mode == 1) rc = raycast_impl(m, max_depth, w, h, K, f.q_xyzw, f.t_xyz, nullptr, nullptr, nullptr, i + 1 < first + count);
     else if (raycast_mode == 2) rc = tsdf_mgpu_raycast_composite(m, max_depth, w, h, K, f.q_xyzw, f.t_xyz, nullptr);
     if (rc) return rc;
   }
+  { int rcb = flush_barrier(m); if (rcb) return rcb; }
   return deferred;
 }
 

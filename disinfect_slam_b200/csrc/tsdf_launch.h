@@ -8,6 +8,7 @@ namespace tsdf {
 
 // kernels_integrate.cu
 void launch_frame_allocate(const DeviceState& S, const FrameParams& P, const FrameInput& in, Texel* tex, cudaStream_t st);
+void launch_insert_candidates(const DeviceState& S, const FrameParams& P, cudaStream_t st);
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int* vis_state, int num_sms,
                            cudaStream_t st);
 void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
@@ -16,10 +17,13 @@ void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const in
 // kernels_raycast.cu
 void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int gen, bool lazy, int num_sms,
                            cudaStream_t st);
+// pulled TSDF cache of a sharded volume (kernels_raycast.cu): local [shard][stride][512] floats + one stamp per slot,
+// the list / counters of the fetch kernels; epoch = content version the stamps must carry, serial = number of this launch
+struct SharedCache { float* cache; int* stamp; int* list; int* count; int stride, epoch, serial, self, pad; };
 void launch_raycast_shared(const PeerView* shards, const PeerView* host_shards, int n_shards, int shard_shift, const FrameParams& P, float step_size,
-                           const SkipMap& M, int row0, int rows, int tile_stride, const float* mirror, int mirror_stride, uchar4* rgba,
-                           uchar4* normal, float* hit_depth, int n_out, void* const* out_rgba, void* const* out_normal,
-                           void* const* out_depth, cudaStream_t st);
+                           const SkipMap& M, int row0, int rows, int tile_stride, const float* mirror, int mirror_stride, const SharedCache& C,
+                           uchar4* rgba, uchar4* normal, float* hit_depth, int n_out, void* const* out_rgba, void* const* out_normal,
+                           void* const* out_depth, int num_sms, cudaStream_t st);
 void launch_raycast(const DeviceState& S, const FrameParams& P, float step_size, const SkipMap& M, uchar4* rgba,
                     uchar4* normal, float* hit_depth, unsigned long long* packed_keys, cudaStream_t st);
 

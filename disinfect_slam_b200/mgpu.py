@@ -43,7 +43,7 @@ SYMBOLS = {
     "tsdf_mgpu_set_profiling": (_i32, [_vp, _i32]),
     "tsdf_mgpu_get_comm_ms": (_i32, [_vp, _vp, _vp]),
 }
-COMM_PHASES = ("broadcast", "barrier", "allgather", "composite_allreduce", "raycast_shared", "gather_sendrecv")
+COMM_PHASES = ("broadcast", "barrier", "allgather", "composite_allreduce", "raycast_shared", "gather_sendrecv", "exchange_barrier")
 
 
 def lib():

@@ -204,6 +204,25 @@ class TSDFGrid:
         arr = (C.c_void_p * len(grids))(*[g.h for g in grids])
         check(self.L.tsdf_peer_attach_local(self.h, len(grids), arr))
 
+    def shared_cache_attach(self, stride_blocks, pad_voxels=3):
+        """Pulled TSDF cache for the shared-volume RayCast (tsdf_shared_cache_attach); 0 blocks detaches."""
+        check(self.L.tsdf_shared_cache_attach(self.h, int(stride_blocks), int(pad_voxels)))
+
+    def shared_cache_fetched(self):
+        """Foreign blocks the most recent shared-volume view fetched into the cache."""
+        n = C.c_int64(0)
+        check(self.L.tsdf_shared_cache_stats(self.h, C.byref(n)))
+        return int(n.value)
+
+    def RayCastSharedScatter(self, max_depth, virtual_cam, cam_T_world, tile_first, tile_stride, tile_count, peers_unchanged, dests):
+        """tsdf_raycast_shared_scatter: `dests` = [(d_rgba, d_normal, d_depth)] device pointers of every destination."""
+        K = _f32(virtual_cam.intrinsics, 4)
+        q, t = _pose(cam_T_world)
+        n = len(dests)
+        arrs = [(C.c_void_p * n)(*[d[i] for d in dests]) for i in range(3)]
+        check(self.L.tsdf_raycast_shared_scatter(self.h, max_depth, int(virtual_cam.img_w), int(virtual_cam.img_h), _p(K), _p(q), _p(t),
+                                                 int(tile_first), int(tile_stride), int(tile_count), int(bool(peers_unchanged)), n, arrs[0], arrs[1], arrs[2]))
+
     def RayCastShared(self, max_depth, virtual_cam, cam_T_world, row0, rows, d_rgba, d_normal, d_depth):
         K = _f32(virtual_cam.intrinsics, 4)
         q, t = _pose(cam_T_world)

@@ -38,7 +38,8 @@ enum {
   TSDF_E_CUDA = -2,           /* CUDA runtime error; see tsdf_last_error() */
   TSDF_E_POOL_EXHAUSTED = -3, /* block pool ran out (reference: device assert, voxel_mem.cu:39) */
   TSDF_E_TABLE_FULL = -4,     /* hash table ran out of slots */
-  TSDF_E_NO_DEVICE = -5       /* no usable CUDA device: the engine never falls back to the CPU */
+  TSDF_E_NO_DEVICE = -5,      /* no usable CUDA device: the engine never falls back to the CPU */
+  TSDF_E_EXCHANGE_FULL = -6   /* candidate exchange of a sharded volume overflowed (tsdf_alloc_exchange_attach: cap_keys) */
 };
 
 typedef struct tsdf_engine* tsdf_handle;
@@ -197,14 +198,16 @@ int tsdf_raycast_shared(tsdf_handle h, float max_depth, int width, int height, c
 /* Same march, with the exchange of the results fused into the kernel: every finished ray is stored into the HxW images
  * of n_dest destinations (device pointers, typically the image buffers of every rank mapped as peer memory; entries or
  * whole arrays may be NULL) -- posted stores over NVLink while the march runs, instead of a local image plus an
- * all-gather afterwards.  The launch renders the 8-row tiles tile_first, tile_first + tile_stride, ... of the view:
- * with tile_first = rank and tile_stride = number of ranks the tiles of a view are dealt out round-robin, so every rank
- * gets the same mix of cheap and expensive rows and all of them finish together.  peers_unchanged != 0: the caller
+ * all-gather afterwards.  The launch renders tile_count (0 = all that remain) of the 8-row tiles tile_first,
+ * tile_first + tile_stride, ... of the view: tile_first = rank, tile_stride = number of ranks deals the tiles of a view
+ * out round-robin (every rank gets the same mix of cheap and expensive rows, but meets almost every visible block);
+ * tile_stride = 1 with tile_count tiles per rank gives every rank one contiguous band of rows, whose rays meet about
+ * 1 / ranks of the visible blocks (what tsdf_shared_cache_attach is made for).  peers_unchanged != 0: the caller
  * vouches that no shard has integrated since this engine's previous shared view (then not even the map-maintenance
  * kernels, which would find nothing to do, are launched).  The caller orders the destinations' readers with its own
  * barrier. */
 int tsdf_raycast_shared_scatter(tsdf_handle h, float max_depth, int width, int height, const float K[4],
-                                const float q_xyzw[4], const float t_xyz[3], int tile_first, int tile_stride,
+                                const float q_xyzw[4], const float t_xyz[3], int tile_first, int tile_stride, int tile_count,
                                 int peers_unchanged, int n_dest, void* const* d_rgba, void* const* d_normal,
                                 void* const* d_hit_depth);
 
@@ -217,6 +220,35 @@ int tsdf_raycast_shared_scatter(tsdf_handle h, float max_depth, int width, int h
  * It trades 2 KB per block of ANY shard on every GPU (a third of the voxel data, replicated) for a march without remote
  * loads.  world == 0 detaches.  Blocks written through tsdf_assign_voxels are not mirrored. */
 int tsdf_mirror_attach(tsdf_handle h, int world, void* const* mirrors, int stride_blocks);
+
+/* Pulled TSDF cache for a sharded volume (optional, the alternative to mirrors; call on an idle engine after the peers
+ * are attached).  The engine allocates a local array of shard_count x stride_blocks x 2 KB (+ 4 B stamps);
+ * stride_blocks >= the largest pool of any shard.  Before every shared-volume march, two small kernels fetch the TSDF
+ * planes of the FOREIGN blocks that the rays of this launch can meet -- a conservative pyramid test of the launch's rows
+ * against every shard's pool directory -- with bulk NVLink reads, and stamp them; the march then samples them locally.
+ * A sample of a foreign block without a current stamp is read from its owner, so results do not depend on the test.
+ * Entries stay valid across views while the caller passes peers_unchanged = 1.  Made for contiguous bands of rows
+ * (tile_stride 1): a rank then fetches about 1/shard_count of the visible blocks per view, whereas mirrors make every
+ * rank receive every update.  pad_voxels = how far the test grows every block (3 covers the nearest-voxel rounding, the
+ * gradient samples and the float accumulation; smaller or negative values are still exact, only slower).
+ * stride_blocks == 0 detaches and frees. */
+int tsdf_shared_cache_attach(tsdf_handle h, int stride_blocks, int pad_voxels);
+/* how many foreign blocks (2 KB each) the most recent shared-volume view of this engine fetched; waits for the stream */
+int tsdf_shared_cache_stats(tsdf_handle h, int64_t* blocks_fetched_last_view);
+
+/* Candidate exchange for a sharded volume (optional; call on an idle engine before the first frame).  Without it every
+ * rank walks the depth band of ALL pixel rays and keeps the candidate blocks it owns (block_allocate_kernel,
+ * voxel_tsdf.cu:104-147, replicated).  With it, rank r stages the whole frame but walks only the rays of every
+ * shard_count-th 32 x 8 pixel tile, and mails each candidate key to its owner: inboxes[o] = rank o's inbox as this GPU
+ * addresses it (peer-mapped; inboxes[shard_rank] is the own one), tsdf_alloc_exchange_bytes(world, cap_keys) bytes,
+ * zero-initialised.  Then the frame hook runs on the engine's stream -- it must publish d_cursor[o] (clamped to cap_keys)
+ * into int word [parity * 8 + shard_rank] of inbox o and order all ranks (a barrier with release / acquire semantics at
+ * system scope) -- and the owner inserts what it received.  All ranks must integrate the same frames in the same order.
+ * Results are those of the unsharded volume.  A rank that would mail more than cap_keys keys to one owner in one frame
+ * reports TSDF_E_EXCHANGE_FULL for that frame.  world == 0 detaches. */
+typedef void (*tsdf_frame_hook)(void* user, void* cuda_stream, const int* d_cursor, int parity);
+size_t tsdf_alloc_exchange_bytes(int world, int cap_keys);
+int tsdf_alloc_exchange_attach(tsdf_handle h, int world, void* const* inboxes, int cap_keys, tsdf_frame_hook hook, void* user);
 
 /* TSDFGrid::GatherValid()                               utils/tsdf/voxel_tsdf.cu:399-425
  * TSDFGrid::GatherVoxels(BoundingCube<float>)           utils/tsdf/voxel_tsdf.cu:427-454

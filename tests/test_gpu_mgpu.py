@@ -77,7 +77,7 @@ def run_rank(rank, world, nccl_id, cfg_name, n_frames):
     return out
 
 
-def check_against_oracle(res, world, cfg, n_frames):
+def check_against_oracle(res, world, cfg, n_frames, exchange_barriers=None):
     from disinfect_slam_b200 import tsdf_grid
     sc = synth.Scene(cfg)
     o = Oracle(cfg.voxel_size, cfg.truncation)
@@ -115,6 +115,8 @@ def check_against_oracle(res, world, cfg, n_frames):
     if world > 1:
         c = res[0]["comm_calls"]
         assert c["broadcast"] == n_frames and c["barrier"] == 3 and c["allgather"] == 3 and c["raycast_shared"] == 3
+        if exchange_barriers is not None:  # candidate exchange: one barrier per frame, between allocate and the owners' inserts
+            assert c["exchange_barrier"] == exchange_barriers
 
 
 def test_data_plane_with_one_shard_matches_oracle(tsdf_lib):
@@ -124,19 +126,31 @@ def test_data_plane_with_one_shard_matches_oracle(tsdf_lib):
     check_against_oracle(res, 1, cfg, N_FRAMES)
 
 
-def _proc(rank, world, nccl_id, q, exchange):
+VARIANTS = {
+    # the product path: peer-barrier kernels, allocation pass sharded by image tiles with the candidate keys mailed to
+    # their owners, one band of rows per rank marched over a pulled TSDF cache, rows stored into every rank's images
+    "fused": {},
+    # round-robin tiles over TSDF mirrors pushed by the integrate kernels, owner-filtered allocation on every rank
+    "fused-push-mirrors": {"TSDF_MGPU_MIRROR": "push", "TSDF_MGPU_ALLOC": "owner"},
+    # no local TSDF copy at all: every foreign sample is a load over NVLink
+    "fused-remote-loads": {"TSDF_MGPU_MIRROR": "0"},
+    # ncclAllReduce barrier + in-place ncclAllGather (kept for comparison)
+    "nccl": {"TSDF_MGPU_EXCHANGE": "nccl"},
+}
+
+
+def _proc(rank, world, nccl_id, q, variant):
     try:
-        os.environ["TSDF_MGPU_EXCHANGE"] = exchange  # read by tsdf_mgpu_create
+        os.environ.update(VARIANTS[variant])  # read by tsdf_mgpu_create
         q.put((rank, run_rank(rank, world, nccl_id, CFG, N_FRAMES)))
     except Exception:
         import traceback
         q.put((rank, {"error": traceback.format_exc()}))
 
 
-@pytest.mark.parametrize("exchange", ["fused", "nccl"])
-def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib, exchange):
-    """exchange = fused: peer-barrier kernels + image rows stored into every rank's buffers by the march kernel (the
-    product path); nccl: ncclAllReduce barrier + in-place ncclAllGather (kept for comparison)."""
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib, variant):
+    """Every variant of the data plane (see VARIANTS) gives the single-volume result, bit for bit."""
     if n_gpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2); the bench's sharded leg carries the driver-visible parity check")
     import multiprocessing as mp
@@ -145,7 +159,7 @@ def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib, exchange):
     nccl_id = mgpu.unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_proc, args=(r, world, nccl_id, q, exchange)) for r in range(world)]
+    procs = [ctx.Process(target=_proc, args=(r, world, nccl_id, q, variant)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -159,7 +173,8 @@ def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib, exchange):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    check_against_oracle(res, world, synth.config(CFG), N_FRAMES)
+    check_against_oracle(res, world, synth.config(CFG), N_FRAMES,
+                         exchange_barriers=N_FRAMES if variant in ("fused", "fused-remote-loads") else 0)
 
 
 def test_two_threads_of_a_pure_cpp_process_match_oracle(tsdf_lib, tmp_path):
