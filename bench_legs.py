@@ -216,13 +216,15 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                               [planes(s) for s in range(n_hist + 3 * K)] if rank == 0 else None)
     import os
 
-    def make_volume(exchange="fused", mirror="pull", alloc="exchange", tiles="interleave"):
+    def make_volume(exchange="fused", mirror="pull", alloc="exchange", tiles="interleave", mode="sharded"):
+        os.environ["TSDF_MGPU_MODE"] = mode
         os.environ["TSDF_MGPU_EXCHANGE"] = exchange  # read by tsdf_mgpu_create
         os.environ["TSDF_MGPU_MIRROR"] = mirror
         os.environ["TSDF_MGPU_ALLOC"] = alloc
         os.environ["TSDF_MGPU_TILES"] = tiles
-        return mgpu.ShardedVolume(VOXEL3, TRUNC3, rank, world, fresh_id(), device=local_rank, pool_blocks=pool_rank,
-                                  table_slots=max(1 << 16, 1 << int(np.ceil(np.log2(4 * pool_rank)))), max_image_pixels=big, shard_shift=2)
+        pool = pool_rank if mode == "sharded" else pool_total
+        return mgpu.ShardedVolume(VOXEL3, TRUNC3, rank, world, fresh_id(), device=local_rank, pool_blocks=pool,
+                                  table_slots=max(1 << 16, 1 << int(np.ceil(np.log2(4 * pool)))), max_image_pixels=big, shard_shift=2)
 
     def seq(first, count, mode):
         vol.run_sequence(0, frames, first, count, Wd, H, MAX_DEPTH3, Kv, raycast_mode=mode, on_device=True)
@@ -265,18 +267,21 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                         "march_with_fused_scatter_us": per(cms_m, cn_m, "raycast_shared"), "peer_barrier_after_march_us": per(cms_m, cn_m, "allgather"),
                         "exchange": "TSDF_MGPU_MIRROR=0 TSDF_MGPU_ALLOC=owner: fused exchange with round-robin tiles, foreign voxels loaded from their owner "
                                     "over NVLink sample by sample, allocation pass replicated on every rank"}
-    # the product path with one contiguous band of rows per rank instead of round-robin tiles
-    vol = make_volume(tiles="band")
-    tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
-    seq(0, n_tour, 0)
-    seq(n_tour, W, 1)
-    ms_b, cms_b, cn_b, _, _ = timed(n_tour + W, K, 1)
-    vol.close()
-    barrier(torch, dist, world)
-    band_variant = {"frames_per_s": K / (ms_b * 1e-3), "us_per_frame": 1e3 * ms_b / K, "peer_barrier_before_march_us": per(cms_b, cn_b, "barrier"),
-                    "march_with_fused_scatter_us": per(cms_b, cn_b, "raycast_shared"), "peer_barrier_after_march_us": per(cms_b, cn_b, "allgather"),
-                    "exchange": "TSDF_MGPU_TILES=band: as the product path, but rank r renders rows [r H/N, (r+1) H/N): fewer foreign blocks to fetch, "
-                                "uneven finishing times"}
+    # the product path with one contiguous band of rows per rank instead of round-robin tiles (TSDF_BENCH_BANDS=1: an extra
+    # volume build; profiles/r2n_bench_*gpu.json hold it for 2 and 4 GPUs)
+    band_variant = None
+    if os.environ.get("TSDF_BENCH_BANDS") == "1":
+        vol = make_volume(tiles="band")
+        tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
+        seq(0, n_tour, 0)
+        seq(n_tour, W, 1)
+        ms_b, cms_b, cn_b, _, _ = timed(n_tour + W, K, 1)
+        vol.close()
+        barrier(torch, dist, world)
+        band_variant = {"frames_per_s": K / (ms_b * 1e-3), "us_per_frame": 1e3 * ms_b / K, "peer_barrier_before_march_us": per(cms_b, cn_b, "barrier"),
+                        "march_with_fused_scatter_us": per(cms_b, cn_b, "raycast_shared"), "peer_barrier_after_march_us": per(cms_b, cn_b, "allgather"),
+                        "exchange": "TSDF_MGPU_TILES=band: as the product path, but rank r renders rows [r H/N, (r+1) H/N): fewer foreign blocks to fetch, "
+                                    "uneven finishing times"}
     # the product path: allocation pass sharded by image tiles (candidate keys mailed to their owners), one band of rows per
     # rank marched over a pulled TSDF cache, rows stored into every rank's images, peer barriers instead of collectives
     vol = make_volume()
@@ -290,6 +295,7 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     img = np.empty((H, Wd, 4), np.uint8), np.empty((H, Wd, 4), np.uint8), np.empty((H, Wd), np.float32)
     mgpu.check(vol.L.tsdf_mgpu_fetch_images(vol.h, img[0].ctypes.data, img[1].ctypes.data, img[2].ctypes.data))
     parity = None
+    want = None
     if rank == 0:
         ref = single_engine_history(n_hist)
         want = ref.RayCast(MAX_DEPTH3, tsdf_grid.CameraParams(Kv, H, Wd), cams[(n_hist - 1) % n_tour])
@@ -346,6 +352,32 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                          "from all shards' directories, fetch of the foreign TSDF planes this rank's band of rows can meet (bulk NVLink reads into a local cache), "
                          "tsdf_raycast_shared_scatter (band of H/N rows, TSDF samples local, hit colours from the owner, finished rays stored into every "
                          "rank's images); CUDA events on the engine stream, max over ranks; voxel updates all-reduced"})
+    # ---- not sharded: a replica of the whole volume on every GPU, whole views dealt round-robin (TSDF_MGPU_MODE=replicas) ----
+    # Every rank integrates every frame (the broadcast is the only thing the ranks share), view k is rendered by rank
+    # k % N into rank 0's memory; no barrier inside the stream.  For volumes that fit one GPU: it multiplies view
+    # throughput, not capacity.
+    vol_s = vol
+    vol = make_volume(mode="replicas")
+    tm_s, tm = tm, DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
+    seq(0, n_tour, 0)
+    seq(n_tour, W, 1)
+    ms_r, cms_r, cn_r, tot_r, n_act_r = timed(n_tour + W, K, 1)
+    img_r = np.empty((H, Wd, 4), np.uint8), np.empty((H, Wd, 4), np.uint8), np.empty((H, Wd), np.float32)
+    parity_r = None
+    if rank == 0:
+        mgpu.check(vol.L.tsdf_mgpu_fetch_images(vol.h, img_r[0].ctypes.data, img_r[1].ctypes.data, img_r[2].ctypes.data))
+        bad = sum(int((a.view(np.uint8) != b.view(np.uint8)).sum()) for a, b in zip(img_r, want))
+        parity_r = "bit-exact" if bad == 0 and n_act_r == n_act else f"MISMATCH: {bad} differing bytes, blocks {n_act_r} vs {n_act}"
+    vol.close()
+    barrier(torch, dist, world)
+    res3["replicated_volume_round_robin_views"] = {
+        "frames_per_s": K / (ms_r * 1e-3), "us_per_frame": 1e3 * ms_r / K, "parity": parity_r,
+        "raycast_mrays_per_s": K * npx / (ms_r * 1e-3) / 1e6, "frame_broadcast_us": per(cms_r, cn_r, "broadcast"),
+        "unique_voxel_updates_per_s": tot_r["n_updated"] / (ms_r * 1e-3),
+        "path": "TSDF_MGPU_MODE=replicas: ncclBroadcast of the planes, every GPU integrates every frame into its own copy of the whole volume "
+                "(the updates are replicated work: only one copy is counted), view k rendered by GPU k mod N straight into rank 0's image memory; "
+                "no barrier between the ranks inside the stream.  Needs the volume to fit one GPU; scales views, not capacity"}
+    vol, tm = vol_s, tm_s
     # config 4 on the sharded volume: exact (rows split) and min-composited (whole views per rank)
     for md in (4.0, 10.0):
         r = {}

@@ -192,7 +192,7 @@ static void enqueue_frame(tsdf_engine* e, const FrameParams& P, const FrameInput
   launch_select_visible(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, e->num_sms, e->stream);
   phase_end(e, PH_SELECT, e->stream);
   phase_begin(e, PH_INTEGRATE, e->stream);
-  launch_integrate_carve(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, f.tex, e->num_sms, e->stream);
+  launch_integrate_carve(e->S, P, e->visible, e->visible + e->cfg.pool_blocks, f.tex, e->num_sms, (int)e->last.n_visible, e->stream);
   phase_end(e, PH_INTEGRATE, e->stream);
   launch_publish_counters(e->S, f.d_h_ctr, e->stream);  // a store into mapped host memory: no copy engine on the compute stream
   cudaEventRecord(f.done, e->stream);

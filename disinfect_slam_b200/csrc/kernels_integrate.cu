@@ -584,13 +584,25 @@ static void launch_integrate_variant(const DeviceState& S, const FrameParams& P,
   integrate_carve_kernel<SLABS, FAST><<<num_sms * ctas_per_sm, 256, 0, st>>>(S, P, visible, vis_state, tex, .9f);
 }
 void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
-                            int num_sms, cudaStream_t st) {
-  // Work-item granularity: whole blocks.  Measured on B200 (config 2, ~11.7 k visible blocks for 4736 resident
-  // warps): 4 slabs per item 46.0 us, 2 slabs 47.9 us, 1 slab 54.2 us -- the per-item set-up costs more than the
-  // shorter tail saves.  SLABS < 4 stays available in the kernel for much smaller frames.
+                            int num_sms, int expected_blocks, cudaStream_t st) {
+  // Work-item granularity.  Measured on B200 (config 2, ~11.7 k visible blocks for 4736 resident warps): whole blocks
+  // (4 slabs per item) 46.0 us, 2 slabs 47.9 us, 1 slab 54.2 us -- with more than two blocks per warp the per-item
+  // set-up costs more than the shorter tail saves.  A shard of a volume spread over many GPUs sees far fewer blocks
+  // than there are resident warps; then a warp's single block IS the kernel's duration and finer items shorten it.
+  // expected_blocks = visible blocks of the most recent finished frame (0 = unknown); the result does not depend on it.
   const bool fast = div_safe_host(P.truncation) && div_safe_host(P.max_depth);
-  if (fast) launch_integrate_variant<4, true>(S, P, visible, vis_state, tex, num_sms, st);
-  else launch_integrate_variant<4, false>(S, P, visible, vis_state, tex, num_sms, st);
+  const int warps = num_sms * 32;  // resident warps at 64 registers per thread
+  const int slabs = expected_blocks <= 0 || expected_blocks > warps ? 4 : expected_blocks > warps / 2 ? 2 : 1;
+  if (slabs == 4) {
+    if (fast) launch_integrate_variant<4, true>(S, P, visible, vis_state, tex, num_sms, st);
+    else launch_integrate_variant<4, false>(S, P, visible, vis_state, tex, num_sms, st);
+  } else if (slabs == 2) {
+    if (fast) launch_integrate_variant<2, true>(S, P, visible, vis_state, tex, num_sms, st);
+    else launch_integrate_variant<2, false>(S, P, visible, vis_state, tex, num_sms, st);
+  } else {
+    if (fast) launch_integrate_variant<1, true>(S, P, visible, vis_state, tex, num_sms, st);
+    else launch_integrate_variant<1, false>(S, P, visible, vis_state, tex, num_sms, st);
+  }
 }
 
 }  // namespace tsdf

@@ -91,6 +91,9 @@ struct tsdf_mgpu {
   bool row_bands = false;                   // one contiguous band of rows per rank instead of 8-row tiles dealt round-robin
   // candidate exchange (tsdf_alloc_exchange_attach): this rank's inbox, every rank's as seen from here, keys per sender
   unsigned char* inbox = nullptr; unsigned char* ipeer[kMaxRanks] = {}; void* iopened[kMaxRanks] = {}; int xa_cap = 0;
+  // TSDF_MGPU_MODE=replicas: every rank keeps the WHOLE volume (an unsharded engine) and integrates every frame; the views
+  // are dealt out round-robin, view k rendered by rank k % world straight into slot [k % world] of rank 0's image memory
+  bool replicas = false; long long view_no = 0; int n_slots = 1; size_t flag_off = 0;
   bool pending_barrier = false;             // run_sequence: the barrier after a view is supplied by the next frame's exchange barrier
   int last_w = 0, last_h = 0;
   unsigned long long* keys = nullptr; size_t keys_cap = 0;
@@ -210,9 +213,14 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
     if (user_cfg->struct_size != (int32_t)sizeof(tsdf_config)) return fail(TSDF_E_INVALID, "tsdf_config.struct_size mismatch");
     cfg = *user_cfg;
   }
-  cfg.shard_rank = rank; cfg.shard_count = world;
   tsdf_mgpu* m = new tsdf_mgpu();
   m->rank = rank; m->world = world;
+  {
+    const char* mode = getenv("TSDF_MGPU_MODE");
+    m->replicas = world > 1 && mode && !strcmp(mode, "replicas");
+  }
+  if (m->replicas) { cfg.shard_rank = 0; cfg.shard_count = 1; cfg.flags &= ~TSDF_FLAG_SHARD_SHIFT_MASK; }
+  else { cfg.shard_rank = rank; cfg.shard_count = world; }
 #define MX(call) do { int r_ = (call); if (r_ != TSDF_OK) { tsdf_mgpu_destroy(m); return r_; } } while (0)
   {
     int rc = tsdf_create(voxel_size, truncation, &cfg, &m->eng);
@@ -245,6 +253,7 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
     CU(cudaMalloc(&m->d_sizes, sizeof(long long) * 64));
     CU(cudaMallocHost(&m->h_sizes, sizeof(long long) * 64));
     // map every shard's table / pool: blobs all-gathered through NCCL
+    if (!m->replicas) {
     unsigned char* d_blobs = nullptr;
     CU(cudaMalloc(&d_blobs, (size_t)TSDF_IPC_BLOB_BYTES * world));
     std::vector<unsigned char> blobs((size_t)TSDF_IPC_BLOB_BYTES * world);
@@ -256,23 +265,26 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
     CU(cudaStreamSynchronize(m->es));
     cudaFree(d_blobs);
     TS(tsdf_ipc_attach(m->eng, world, blobs.data()));
+    }
     // exchange buffer (images + barrier flags) of every rank, mapped the same way
     m->img_stride = 4 * (m->max_px + kRowSlack);
-    CU(cudaMalloc(&m->xbuf, 3 * m->img_stride + kFlagBytes));
-    CU(cudaMemsetAsync(m->xbuf, 0, 3 * m->img_stride + kFlagBytes, m->es));
+    m->n_slots = m->replicas ? world : 1;   // replicas: one image set per rendering rank (only rank 0's copy is used)
+    m->flag_off = 3 * m->img_stride * (size_t)m->n_slots;  // the same layout on every rank
+    CU(cudaMalloc(&m->xbuf, m->flag_off + kFlagBytes));
+    CU(cudaMemsetAsync(m->xbuf, 0, m->flag_off + kFlagBytes, m->es));
     CU(cudaMalloc(&m->d_err, sizeof(int)));
     CU(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->es));
     for (int i = 0; i < 3; ++i) m->img[i] = m->xbuf + (size_t)i * m->img_stride;
     {
       const char* ex = getenv("TSDF_MGPU_EXCHANGE");
-      m->fused = !(ex && !strcmp(ex, "nccl"));
+      m->fused = m->replicas || !(ex && !strcmp(ex, "nccl"));
       // How the march gets at foreign TSDF samples.  Default: pulled cache (before the march every rank fetches the TSDF
       // planes of the foreign blocks its rays can meet: about a room's worth, a few MB).  TSDF_MGPU_MIRROR=push: mirrors
       // written by the owners' integrate kernels (every rank receives every update of every frame: NVLink-ingress bound
       // beyond 2 GPUs); =0: neither, every foreign sample is a load over NVLink.  The NCCL-exchange variant keeps the
       // plain form.
       const char* mi = getenv("TSDF_MGPU_MIRROR");
-      m->mirror_mode = world < 2 ? 0 : (mi && !strcmp(mi, "0")) ? 0 : (mi && !strcmp(mi, "push")) ? 1 : (mi && !strcmp(mi, "pull")) ? 2 : (m->fused ? 2 : 0);
+      m->mirror_mode = world < 2 || m->replicas ? 0 : (mi && !strcmp(mi, "0")) ? 0 : (mi && !strcmp(mi, "push")) ? 1 : (mi && !strcmp(mi, "pull")) ? 2 : (m->fused ? 2 : 0);
       const bool want_mirror = m->mirror_mode == 1;
       // Which rows a rank renders: 8-row tiles dealt round-robin (default: every rank gets the same mix of cheap and
       // expensive rows) or TSDF_MGPU_TILES=band, one contiguous band per rank (fewer foreign blocks to fetch, but the
@@ -281,7 +293,7 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
       m->row_bands = ti && !strcmp(ti, "band");
       // Candidate exchange (allocation pass sharded by image tiles): needs the peer barrier, i.e. the fused plane
       const char* al = getenv("TSDF_MGPU_ALLOC");
-      const bool want_exchange = world > 1 && m->fused && !(al && !strcmp(al, "owner"));
+      const bool want_exchange = world > 1 && m->fused && !m->replicas && !(al && !strcmp(al, "owner"));
       std::vector<XBlob> xb(world);
       XBlob mine{};
       CU(cudaIpcGetMemHandle(&mine.h, m->xbuf));
@@ -422,7 +434,7 @@ static int ensure_images(tsdf_mgpu* m, int w, int h) {
 
 static int peer_barrier(tsdf_mgpu* m, const int* d_cursor = nullptr, int parity = 0) {
   PeerFlags pf{};
-  for (int r = 0; r < m->world; ++r) pf.flags[r] = reinterpret_cast<int*>(m->xpeer[r] + 3 * m->img_stride);
+  for (int r = 0; r < m->world; ++r) pf.flags[r] = reinterpret_cast<int*>(m->xpeer[r] + m->flag_off);
   PeerCounts mail{};
   if (d_cursor) {
     mail.cursor = d_cursor; mail.slot = parity * 8 + m->rank; mail.cap = m->xa_cap;
@@ -462,7 +474,22 @@ static int raycast_impl(tsdf_mgpu_handle m, float max_depth, int w, int h, const
   int rc = ensure_images(m, w, h);
   if (rc) return rc;
   const int rows = rows_per_rank(m, h), row0 = m->rank * rows;
-  if (m->world > 1 && m->fused) {
+  if (m->replicas) {
+    // whole views dealt round-robin over the replicas: no rank waits for another one.  The renderer writes the view
+    // straight into its slot of rank 0's image memory (posted stores over NVLink); views of one renderer are ordered by
+    // its stream, views of different renderers use different slots.
+    const int renderer = (int)(m->view_no % m->world);
+    m->view_no++;
+    if (m->rank == renderer) {
+      Timed tm(m, T_RAYCAST, m->es);
+      unsigned char* slot = m->xpeer[0] + 3 * m->img_stride * (size_t)renderer;
+      TS(tsdf_raycast_device(m->eng, max_depth, w, h, K, q, t, slot, slot + m->img_stride, slot + 2 * m->img_stride, nullptr));
+    }
+    // a barrier makes every view issued so far complete on rank 0 (inside tsdf_mgpu_run_sequence: only after the last one)
+    if (!defer_barrier) { Timed tm(m, T_ALLGATHER, m->es); int rc2 = peer_barrier(m); if (rc2) return rc2; }
+    unsigned char* last = m->xbuf + 3 * m->img_stride * (size_t)renderer;
+    for (int i = 0; i < 3; ++i) m->img[i] = last + (size_t)i * m->img_stride;
+  } else if (m->world > 1 && m->fused) {
     // fused exchange: no collective library on the engine stream.  Barrier (every shard's Integrate has finished before
     // any rank reads its voxels) -> march with the finished rays stored into every rank's images -> barrier (all rows
     // have arrived everywhere, and every peer is done reading this rank's voxels before its next Integrate)
@@ -515,6 +542,7 @@ int tsdf_mgpu_raycast_composite(tsdf_mgpu_handle m, float max_depth, int w, int 
   if (!m || !K || !q || !t) return fail(TSDF_E_INVALID, "null argument");
   if (w <= 0 || h <= 0) return fail(TSDF_E_INVALID, "bad image size %dx%d", w, h);
   CU(cudaSetDevice(m->device));
+  if (m->replicas) return fail(TSDF_E_INVALID, "min-compositing is for a sharded volume; replicas render whole views (tsdf_mgpu_raycast)");
   { int rcb = flush_barrier(m); if (rcb) return rcb; }
   const size_t need = 2 * (size_t)w * h;
   if (need > m->keys_cap) {
@@ -556,11 +584,16 @@ int tsdf_mgpu_gather(tsdf_mgpu_handle m, int root, const float* bbox, float* out
   TS(tsdf_gather_device_result(m->eng, &d_mine, nullptr));
   // sizes first
   m->h_sizes[m->rank] = mine;
-  if (m->world > 1) {
+  if (m->world > 1 && !m->replicas) {
     CU(cudaMemcpyAsync(m->d_sizes + m->rank, m->h_sizes + m->rank, sizeof(long long), cudaMemcpyHostToDevice, m->es));
     NC(ncclAllGather(m->d_sizes + m->rank, m->d_sizes, 1, ncclInt64, m->comm_sync, m->es));
     CU(cudaMemcpyAsync(m->h_sizes, m->d_sizes, sizeof(long long) * m->world, cudaMemcpyDeviceToHost, m->es));
     CU(cudaStreamSynchronize(m->es));
+  }
+  if (m->replicas) {  // every rank holds the whole volume: the root answers from its own
+    if (n_voxels) *n_voxels = mine;
+    if (m->rank == root && out && cap > 0) TS(tsdf_gather_fetch(m->eng, out, cap));
+    return TSDF_OK;
   }
   int64_t total = 0;
   for (int r = 0; r < m->world; ++r) total += m->h_sizes[r];
@@ -615,7 +648,7 @@ int tsdf_mgpu_counters(tsdf_mgpu_handle m, tsdf_counters* last_sum, tsdf_counter
   memcpy(h, &last, sizeof(last));
   memcpy(h + 8, &tot, sizeof(tot));
   h[16] = act;
-  if (m->world > 1) {
+  if (m->world > 1 && !m->replicas) {  // (a replica's counters already describe the whole volume)
     CU(cudaMemcpyAsync(m->d_sizes, h, sizeof(long long) * 17, cudaMemcpyHostToDevice, m->es));
     NC(ncclAllReduce(m->d_sizes, m->d_sizes, 17, ncclInt64, ncclSum, m->comm_sync, m->es));
     CU(cudaMemcpyAsync(h, m->d_sizes, sizeof(long long) * 17, cudaMemcpyDeviceToHost, m->es));

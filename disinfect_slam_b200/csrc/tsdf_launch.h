@@ -12,7 +12,7 @@ void launch_insert_candidates(const DeviceState& S, const FrameParams& P, cudaSt
 void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visible, int* vis_state, int num_sms,
                            cudaStream_t st);
 void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
-                            int num_sms, cudaStream_t st);
+                            int num_sms, int expected_blocks, cudaStream_t st);
 
 // kernels_raycast.cu
 void launch_build_skip_map(const PeerView* shards, int n_shards, const SkipMap& M, int gen, bool lazy, int num_sms,

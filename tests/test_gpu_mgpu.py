@@ -77,6 +77,32 @@ def run_rank(rank, world, nccl_id, cfg_name, n_frames):
     return out
 
 
+def check_replicas_against_oracle(res, world, cfg, n_frames):
+    """TSDF_MGPU_MODE=replicas: every rank holds the whole volume; view k is rendered by rank k % world into rank 0's memory."""
+    sc = synth.Scene(cfg)
+    o = Oracle(cfg.voxel_size, cfg.truncation)
+    for i in range(n_frames):
+        f = sc.frame(i)
+        oc = o.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"])
+        if i == 1:
+            ref_mid = o.raycast(cfg.max_depth, cfg.width, cfg.height, f["K"], f["q"], f["t"])[:3]
+    ok, ot, oc_, op = o.export()
+    for r in range(world):
+        assert np.array_equal(res[r]["keys"], ok), f"replica {r}: block set"
+        assert np.array_equal(res[r]["tsdf"].view(np.uint32), ot.view(np.uint32)) and np.array_equal(res[r]["rgbw"], oc_)
+        assert np.abs(res[r]["prob"] - op).max() <= compare.PROB_TOL
+        last = res[r]["last"]
+        assert (last["n_new"], last["n_visible"], last["n_updated"], last["n_carved"]) == (oc["n_new"], oc["n_vis"], oc["n_upd"], oc["n_carved"])
+        assert res[r]["n_active"] == len(ok)
+    # the images live on rank 0 whoever rendered them: views 0 (rank 0), 1 (rank 1), 2 (rank 0)
+    compare.compare_raycast(res[0]["mid"], ref_mid, "mid-stream view (rendered by rank 0)")
+    compare.compare_raycast(res[0]["exact"], o.raycast(cfg.max_depth, cfg.width, cfg.height, f["K"], f["q"], f["t"])[:3], "view rendered by rank 1")
+    compare.compare_raycast(res[0]["exact10"], o.raycast(10.0, cfg.width, cfg.height, f["K"], f["q"], f["t"])[:3], "max_depth 10 view")
+    assert compare.compare_gather(res[0]["gathered"], o.gather(), "replica GatherValid")["tsdf_bit_exact"]
+    assert [res[r]["comm_calls"]["raycast_shared"] for r in range(world)] == [2, 1]
+    assert res[0]["comm_calls"]["broadcast"] == n_frames and res[0]["comm_calls"]["exchange_barrier"] == 0
+
+
 def check_against_oracle(res, world, cfg, n_frames, exchange_barriers=None):
     from disinfect_slam_b200 import tsdf_grid
     sc = synth.Scene(cfg)
@@ -136,6 +162,9 @@ VARIANTS = {
     "fused-remote-loads": {"TSDF_MGPU_MIRROR": "0"},
     # ncclAllReduce barrier + in-place ncclAllGather (kept for comparison)
     "nccl": {"TSDF_MGPU_EXCHANGE": "nccl"},
+    # not sharded at all: every GPU integrates every frame into its own copy of the whole volume, whole views are dealt
+    # round-robin (throughput for volumes that fit one GPU)
+    "replicas": {"TSDF_MGPU_MODE": "replicas"},
 }
 
 
@@ -173,8 +202,11 @@ def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib, variant):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    check_against_oracle(res, world, synth.config(CFG), N_FRAMES,
-                         exchange_barriers=N_FRAMES if variant in ("fused", "fused-remote-loads") else 0)
+    if variant == "replicas":
+        check_replicas_against_oracle(res, world, synth.config(CFG), N_FRAMES)
+    else:
+        check_against_oracle(res, world, synth.config(CFG), N_FRAMES,
+                             exchange_barriers=N_FRAMES if variant in ("fused", "fused-remote-loads") else 0)
 
 
 def test_two_threads_of_a_pure_cpp_process_match_oracle(tsdf_lib, tmp_path):
