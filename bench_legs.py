@@ -216,7 +216,7 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                               [planes(s) for s in range(n_hist + 3 * K)] if rank == 0 else None)
     import os
 
-    def make_volume(exchange="fused", mirror="pull", alloc="exchange", tiles="interleave", mode="sharded"):
+    def make_volume(exchange="fused", mirror="push", alloc="owner", tiles="interleave", mode="sharded"):
         os.environ["TSDF_MGPU_MODE"] = mode
         os.environ["TSDF_MGPU_EXCHANGE"] = exchange  # read by tsdf_mgpu_create
         os.environ["TSDF_MGPU_MIRROR"] = mirror
@@ -254,9 +254,9 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     nccl_variant = {"frames_per_s": K / (ms_n * 1e-3), "us_per_frame": 1e3 * ms_n / K, "barrier_allreduce_us": per(cms_n, cn_n, "barrier"),
                     "image_allgather_us": per(cms_n, cn_n, "allgather"), "raycast_shared_kernels_us": per(cms_n, cn_n, "raycast_shared"),
                     "exchange": "TSDF_MGPU_EXCHANGE=nccl: 4-byte ncclAllReduce, march into a local image, grouped in-place ncclAllGather of 12 B/px"}
-    # fused exchange in its first form: 8-row tiles dealt round-robin, every TSDF sample of a foreign block loaded over NVLink,
-    # every rank walks all pixel rays in the allocation pass
-    vol = make_volume("fused", mirror="0", alloc="owner")
+    # alternative form of the fused plane: allocation pass sharded by image tiles (candidate keys mailed to their owners, one more
+    # peer barrier per frame), foreign TSDF planes fetched into a local cache before the march instead of pushed mirrors
+    vol = make_volume("fused", mirror="pull", alloc="exchange")
     tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
     seq(0, n_tour, 0)
     seq(n_tour, W, 1)
@@ -265,13 +265,15 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     barrier(torch, dist, world)
     nomirror_variant = {"frames_per_s": K / (ms_m * 1e-3), "us_per_frame": 1e3 * ms_m / K, "peer_barrier_before_march_us": per(cms_m, cn_m, "barrier"),
                         "march_with_fused_scatter_us": per(cms_m, cn_m, "raycast_shared"), "peer_barrier_after_march_us": per(cms_m, cn_m, "allgather"),
-                        "exchange": "TSDF_MGPU_MIRROR=0 TSDF_MGPU_ALLOC=owner: fused exchange with round-robin tiles, foreign voxels loaded from their owner "
-                                    "over NVLink sample by sample, allocation pass replicated on every rank"}
+                        "peer_barrier_candidate_exchange_us": per(cms_m, cn_m, "exchange_barrier"),
+                        "exchange": "TSDF_MGPU_MIRROR=pull TSDF_MGPU_ALLOC=exchange: pixel rays walked on 1/N of the 32x8 tiles per rank, candidate keys mailed to "
+                                    "their owners' inboxes, peer barrier, owners insert; before the march the foreign TSDF planes the view can meet are fetched "
+                                    "into a local cache (bulk NVLink reads) instead of being pushed by the integrate kernels"}
     # the product path with one contiguous band of rows per rank instead of round-robin tiles (TSDF_BENCH_BANDS=1: an extra
     # volume build; profiles/r2n_bench_*gpu.json hold it for 2 and 4 GPUs)
     band_variant = None
     if os.environ.get("TSDF_BENCH_BANDS") == "1":
-        vol = make_volume(tiles="band")
+        vol = make_volume(mirror="pull", alloc="exchange", tiles="band")
         tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
         seq(0, n_tour, 0)
         seq(n_tour, W, 1)
@@ -282,8 +284,8 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                         "march_with_fused_scatter_us": per(cms_b, cn_b, "raycast_shared"), "peer_barrier_after_march_us": per(cms_b, cn_b, "allgather"),
                         "exchange": "TSDF_MGPU_TILES=band: as the product path, but rank r renders rows [r H/N, (r+1) H/N): fewer foreign blocks to fetch, "
                                     "uneven finishing times"}
-    # the product path: allocation pass sharded by image tiles (candidate keys mailed to their owners), one band of rows per
-    # rank marched over a pulled TSDF cache, rows stored into every rank's images, peer barriers instead of collectives
+    # the product path: owner-filtered allocation, TSDF mirrors kept current by the integrate kernels, round-robin tiles marched
+    # locally, rows stored into every rank's images, peer barriers instead of collectives
     vol = make_volume()
     tm = DeviceTimer(torch, tsdf_grid._lib.lib().tsdf_stream(vol.engine), dev)
     seq(0, n_tour, 0)          # the tour that builds the volume
@@ -316,10 +318,11 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
     fetched = C.c_int64(0)
     tsdf_grid._lib.check(L0.tsdf_shared_cache_stats(vol.engine, C.byref(fetched)))
     tsdf_grid._lib.check(L0.tsdf_set_profiling(vol.engine, 0))
-    phases = {n: (1e3 * pms[i] / pcnt[i] if pcnt[i] else None) for i, n in ((1, "stage_and_walk_rays_us"), (2, "insert_candidates_and_select_us"), (3, "integrate_us"),
-                                                                            (4, "map_fetch_march_scatter_us"))}
-    phases["tsdf_blocks_fetched_last_view"] = int(fetched.value)
-    phases["note"] = f"rank {rank}'s engine stream, CUDA events; the fetch moves 2 KB per block over NVLink"
+    phases = {n: (1e3 * pms[i] / pcnt[i] if pcnt[i] else None) for i, n in ((1, "stage_and_allocate_us"), (2, "select_us"), (3, "integrate_us"),
+                                                                            (4, "map_march_scatter_us"))}
+    if fetched.value:
+        phases["tsdf_blocks_fetched_last_view"] = int(fetched.value)
+    phases["note"] = f"rank {rank}'s engine stream, CUDA events"
     ms_int, cms_i, cn_i, tot_i, _ = timed(n_hist + K, K, 0)
     ms_cmp, cms_c, cn_c, _, _ = timed(n_hist + 2 * K, K, 2)
     coll = {"frame_broadcast_us": per(cms, cn, "broadcast"), "peer_barrier_candidate_exchange_us": per(cms, cn, "exchange_barrier"),
@@ -345,12 +348,11 @@ def config3_and_4(args, cfg2, st0, d0, rank, world, local_rank, dev, n_frames, W
                                     "broadcast_us": per(cms_i, cn_i, "broadcast")},
                  "integrate_raycast_min_composite": {"frames_per_s": K / (ms_cmp * 1e-3), "us_per_frame": 1e3 * ms_cmp / K},
                  "collectives": coll, "limiting_collective": max(on_path, key=on_path.get), "engine_phases": phases,
-                 "nccl_exchange_variant": nccl_variant, "round_robin_remote_loads_variant": nomirror_variant, "row_bands_variant": band_variant,
+                 "nccl_exchange_variant": nccl_variant, "pull_cache_candidate_exchange_variant": nomirror_variant, "row_bands_variant": band_variant,
                  "path": "libtsdf_b200_mgpu.so: tsdf_mgpu_run_sequence (C++ loop, NCCL linked directly): grouped ncclBroadcast of the planes from rank 0's HBM, "
-                         "frame staged everywhere, pixel rays walked on 1/N of the 32x8 tiles per rank with the candidate keys mailed to their owners' inboxes "
-                         "(NVLink stores), peer barrier kernel (also closes the previous view), owners insert, select + integrate; peer barrier kernel, skip map "
-                         "from all shards' directories, fetch of the foreign TSDF planes this rank's band of rows can meet (bulk NVLink reads into a local cache), "
-                         "tsdf_raycast_shared_scatter (band of H/N rows, TSDF samples local, hit colours from the owner, finished rays stored into every "
+                         "owner-filtered allocate + integrate (every updated TSDF value also stored into all ranks' TSDF mirrors: posted NVLink stores), "
+                         "peer barrier kernel, skip map from all shards' directories, tsdf_raycast_shared_scatter (1/N of the 8-row tiles, dealt round-robin; "
+                         "TSDF samples from the local mirror, hit colours from the owner, finished rays stored into every "
                          "rank's images); CUDA events on the engine stream, max over ranks; voxel updates all-reduced"})
     # ---- not sharded: a replica of the whole volume on every GPU, whole views dealt round-robin (TSDF_MGPU_MODE=replicas) ----
     # Every rank integrates every frame (the broadcast is the only thing the ranks share), view k is rendered by rank

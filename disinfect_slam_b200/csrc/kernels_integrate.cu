@@ -371,7 +371,7 @@ __device__ __forceinline__ void update_exact(const FrameParams& P, float sdf, ui
   rgbw = min(r, 255u) | (min(g, 255u) << 8) | (min(b, 255u) << 16) | (w << 24);
 }
 
-template <int SLABS, bool FAST>
+template <int SLABS, bool FAST, bool MIRROR>
 __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kernel(DeviceState S, FrameParams P,
                                                               const int* __restrict__ visible, int* __restrict__ vis_state,
                                                               const Texel* __restrict__ tex, float carve_threshold) {
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256, INTEGRATE_MIN_CTAS) integrate_carve_kerne
       item_min = fminf(item_min, fminf(fminf(fabsf(tsdf[0]), fabsf(tsdf[1])), fminf(fabsf(tsdf[2]), fabsf(tsdf[3]))));
       if ((upd & 15u) || is_new) {  // a block that turns out to be carved is released anyway: writing it is harmless
         st16(base_tsdf + slab * 128, make_float4(tsdf[0], tsdf[1], tsdf[2], tsdf[3]));
-        if (S.n_mirror) {  // sharded volume: the same 16 bytes into every rank's TSDF mirror (posted stores over NVLink)
+        if (MIRROR && S.n_mirror) {  // (its own instantiation: the single-GPU kernel carries none of this) sharded volume: the same 16 bytes into every rank's TSDF mirror (posted stores over NVLink)
           const size_t slot = ((size_t)S.shard_rank * S.mirror_stride + idx) * kBlockVolume + lane * 4 + slab * 128;
           for (int r = 0; r < S.n_mirror; ++r) st16(S.mirror[r] + slot, make_float4(tsdf[0], tsdf[1], tsdf[2], tsdf[3]));
         }
@@ -569,19 +569,25 @@ void launch_select_visible(const DeviceState& S, const FrameParams& P, int* visi
   select_visible_kernel<<<num_sms * 4, 256, 0, st>>>(S, P, visible, vis_state);
 }
 static bool div_safe_host(float b) { return b > 9.5367431640625e-07f && b < 1048576.f; }  // div_safe of tsdf_device.cuh
-template <int SLABS, bool FAST>
-static void launch_integrate_variant(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
+template <int SLABS, bool FAST, bool MIRROR>
+static void launch_integrate_mirror_variant(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
                                      int num_sms, cudaStream_t st) {
   // persistent warps: exactly the resident CTAs, work comes from the device-side queue (engines on several host threads
   // may race to fill this in: they all compute the same value)
   static std::atomic<int> cached{0};
   int ctas_per_sm = cached.load(std::memory_order_relaxed);
   if (ctas_per_sm == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, integrate_carve_kernel<SLABS, FAST>, 256, 0) != cudaSuccess || ctas_per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, integrate_carve_kernel<SLABS, FAST, MIRROR>, 256, 0) != cudaSuccess || ctas_per_sm < 1)
       ctas_per_sm = 2;
     cached.store(ctas_per_sm, std::memory_order_relaxed);
   }
-  integrate_carve_kernel<SLABS, FAST><<<num_sms * ctas_per_sm, 256, 0, st>>>(S, P, visible, vis_state, tex, .9f);
+  integrate_carve_kernel<SLABS, FAST, MIRROR><<<num_sms * ctas_per_sm, 256, 0, st>>>(S, P, visible, vis_state, tex, .9f);
+}
+template <int SLABS, bool FAST>
+static void launch_integrate_variant(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
+                                     int num_sms, cudaStream_t st) {
+  if (S.n_mirror) launch_integrate_mirror_variant<SLABS, FAST, true>(S, P, visible, vis_state, tex, num_sms, st);
+  else launch_integrate_mirror_variant<SLABS, FAST, false>(S, P, visible, vis_state, tex, num_sms, st);
 }
 void launch_integrate_carve(const DeviceState& S, const FrameParams& P, const int* visible, int* vis_state, const Texel* tex,
                             int num_sms, int expected_blocks, cudaStream_t st) {

@@ -49,25 +49,30 @@ __device__ __forceinline__ Planes planes_of(const SkipMap& M, int gen) {
 // Every thread derives the same header from the AABB counters (a handful of integer operations), so that no separate
 // one-thread launch is needed; thread 0 publishes it for the later kernels.
 __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restrict__ shards, int n_shards, SkipMap M, int gen, int lazy) {
+  // The persistent counters of every shard (serial of the last block-set change, high-water mark, AABB) first, all at
+  // once: for foreign shards each is a load over NVLink, and fetched one after the other inside the loops below they
+  // cost one round trip per shard and loop -- ~25 us of pure latency on 8 GPUs.
+  __shared__ int s_ctr[kMaxPeers][C_PER_CALL];
+  if ((int)threadIdx.x < n_shards * C_PER_CALL) s_ctr[threadIdx.x / C_PER_CALL][threadIdx.x % C_PER_CALL] = shards[threadIdx.x / C_PER_CALL].ctr[threadIdx.x % C_PER_CALL];
+  __syncthreads();
   {
     int* const now = M.hdr + kSkipSigBase + (gen & 1) * kSkipSigInts;
     const int* const before = M.hdr + kSkipSigBase + ((gen - 1) & 1) * kSkipSigInts;
     bool rebuild = !lazy || before[0] != n_shards;
-    for (int r = 0; r < n_shards; ++r) rebuild = rebuild || before[1 + r] != shards[r].ctr[C_DIRTY];
+    for (int r = 0; r < n_shards; ++r) rebuild = rebuild || before[1 + r] != s_ctr[r][C_DIRTY];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       now[0] = n_shards;
-      for (int r = 0; r < n_shards; ++r) now[1 + r] = shards[r].ctr[C_DIRTY];
+      for (int r = 0; r < n_shards; ++r) now[1 + r] = s_ctr[r][C_DIRTY];
       M.hdr[10 + (gen & 1)] = rebuild ? 1 : 0;
       M.hdr[8 + (gen & 1)] = M.hdr[8 + ((gen - 1) & 1)] + (rebuild ? 1 : 0);
       if (rebuild) M.hdr[12]++;
     }
     if (!rebuild) return;
   }
-  // AABB of every shard's inserts (one shard = the engine itself; several = a volume sharded over GPUs, whose
-  // counters are read over NVLink)
+  // AABB of every shard's inserts (one shard = the engine itself; several = a volume sharded over GPUs)
   int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, z0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF, y1 = -0x7FFFFFFF, z1 = -0x7FFFFFFF;
   for (int r = 0; r < n_shards; ++r) {
-    const int* c = shards[r].ctr;
+    const int* c = s_ctr[r];
     x0 = min(x0, c[C_MIN_X]); y0 = min(y0, c[C_MIN_Y]); z0 = min(z0, c[C_MIN_Z]);
     x1 = max(x1, c[C_MAX_X]); y1 = max(y1, c[C_MAX_Y]); z1 = max(z1, c[C_MAX_Z]);
   }
@@ -87,20 +92,26 @@ __global__ void __launch_bounds__(256) skip_mark_kernel(const PeerView* __restri
   }
   if (n == 0) return;
   unsigned char* const plane = planes_of(M, gen).mark;  // all cells at the cap (see above)
-  for (int r = 0; r < n_shards; ++r) {
-    const int hw = shards[r].ctr[C_HIGH_WATER];
-    const u64* dir = shards[r].block_key;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
-      const u64 k = dir[i];
-      if (k == kEmpty) continue;
-      int bx, by, bz; unpack_key(k, bx, by, bz);
-      const int cx = (bx - x0) >> shift, cy = (by - y0) >> shift, cz = (bz - z0) >> shift;
-      const size_t cell = ((size_t)cz * ny + cy) * nx + cx;
-      plane[cell] = 0;
-      // occupied cell: >= 0.  One cell = one block (shift 0): owner shard << kIndexShardShift | pool index (the directory
-      // position IS the pool index), so the ray caster needs no table probe; coarser cells: 0, the caster probes the table
-      M.cells[cell] = shift == 0 ? ((r << kIndexShardShift) | i) : 0;
-    }
+  // one index space over the directories of all shards, so that a thread reads about ONE entry (a remote load for a
+  // foreign shard) instead of one per shard, one after the other
+  int first[kMaxPeers + 1];
+  first[0] = 0;
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r) first[r + 1] = first[r] + (r < n_shards ? s_ctr[r][C_HIGH_WATER] : 0);
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < first[kMaxPeers]; g += gridDim.x * blockDim.x) {
+    int r = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxPeers; ++q) r += g >= first[q] ? 1 : 0;
+    const int i = g - first[r];
+    const u64 k = shards[r].block_key[i];
+    if (k == kEmpty) continue;
+    int bx, by, bz; unpack_key(k, bx, by, bz);
+    const int cx = (bx - x0) >> shift, cy = (by - y0) >> shift, cz = (bz - z0) >> shift;
+    const size_t cell = ((size_t)cz * ny + cy) * nx + cx;
+    plane[cell] = 0;
+    // occupied cell: >= 0.  One cell = one block (shift 0): owner shard << kIndexShardShift | pool index (the directory
+    // position IS the pool index), so the ray caster needs no table probe; coarser cells: 0, the caster probes the table
+    M.cells[cell] = shift == 0 ? ((r << kIndexShardShift) | i) : 0;
   }
 }
 
@@ -344,43 +355,49 @@ __global__ void __launch_bounds__(256) pull_select_kernel(const PeerView* __rest
   const unsigned lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) count[(serial + 1) & 3] = 0;  // the next launch's counter (nobody touches it now)
   int* const n_listed = count + (serial & 3);
-  for (int r = 0; r < n_shards; ++r) {
-    if (r == self) continue;
-    const int hw = shards[r].ctr[C_HIGH_WATER];
-    const u64* dir = shards[r].block_key;
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < hw; base += gridDim.x * blockDim.x) {
-      const int i = base + (int)lane;
-      bool want = false;
-      if (i < hw && i < stride) {
-        const u64 k = dir[i];
-        if (k != kEmpty && stamp[(size_t)r * stride + i] != epoch) {
-          int bx, by, bz; unpack_key(k, bx, by, bz);
-          unsigned beyond = 0x3Fu;  // bit p: every corner so far lies beyond plane p
+  __shared__ int s_hw[kMaxPeers];  // every shard's high-water mark in one round trip (see skip_mark_kernel)
+  if ((int)threadIdx.x < n_shards) s_hw[threadIdx.x] = shards[threadIdx.x].ctr[C_HIGH_WATER];
+  __syncthreads();
+  int first[kMaxPeers + 1];  // one index space over the foreign directories: about one (remote) entry per thread
+  first[0] = 0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float wx = (float)((bx << 3) + ((c & 1) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
-            const float wy = (float)((by << 3) + ((c & 2) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
-            const float wz = (float)((bz << 3) + ((c & 4) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
-            const float3 q = apply(P.cam_T_world, f3(wx, wy, wz));
-            unsigned in = 0u;
-            if (!(q.x - F.xlo * q.z < 0.f)) in |= 1u;
-            if (!(q.x - F.xhi * q.z > 0.f)) in |= 2u;
-            if (!(q.y - F.ylo * q.z < 0.f)) in |= 4u;
-            if (!(q.y - F.yhi * q.z > 0.f)) in |= 8u;
-            if (!(q.z < 0.f)) in |= 16u;
-            if (!(q.z > F.zfar)) in |= 32u;
-            beyond &= ~in;
-          }
-          want = beyond == 0u;
+  for (int r = 0; r < kMaxPeers; ++r) first[r + 1] = first[r] + (r < n_shards && r != self ? min(s_hw[r], stride) : 0);
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < first[kMaxPeers]; base += gridDim.x * blockDim.x) {
+    const int g = base + (int)lane;
+    bool want = false;
+    int r = 0, i = 0;
+    if (g < first[kMaxPeers]) {
+#pragma unroll
+      for (int q = 1; q < kMaxPeers; ++q) r += g >= first[q] ? 1 : 0;
+      i = g - first[r];
+      const u64 k = shards[r].block_key[i];
+      if (k != kEmpty && stamp[(size_t)r * stride + i] != epoch) {
+        int bx, by, bz; unpack_key(k, bx, by, bz);
+        unsigned beyond = 0x3Fu;  // bit p: every corner so far lies beyond plane p
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float wx = (float)((bx << 3) + ((c & 1) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
+          const float wy = (float)((by << 3) + ((c & 2) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
+          const float wz = (float)((bz << 3) + ((c & 4) ? kBlockLen - 1 + pad : -pad)) * P.voxel_size;
+          const float3 q = apply(P.cam_T_world, f3(wx, wy, wz));
+          unsigned in = 0u;
+          if (!(q.x - F.xlo * q.z < 0.f)) in |= 1u;
+          if (!(q.x - F.xhi * q.z > 0.f)) in |= 2u;
+          if (!(q.y - F.ylo * q.z < 0.f)) in |= 4u;
+          if (!(q.y - F.yhi * q.z > 0.f)) in |= 8u;
+          if (!(q.z < 0.f)) in |= 16u;
+          if (!(q.z > F.zfar)) in |= 32u;
+          beyond &= ~in;
         }
+        want = beyond == 0u;
       }
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
-      if (m) {
-        int off = 0;
-        if (lane == (unsigned)(__ffs(m) - 1)) off = atomicAdd(n_listed, __popc(m));
-        off = __shfl_sync(0xFFFFFFFFu, off, __ffs(m) - 1);
-        if (want) list[off + __popc(m & ((1u << lane) - 1u))] = (r << kIndexShardShift) | i;
-      }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+    if (m) {
+      int off = 0;
+      if (lane == (unsigned)(__ffs(m) - 1)) off = atomicAdd(n_listed, __popc(m));
+      off = __shfl_sync(0xFFFFFFFFu, off, __ffs(m) - 1);
+      if (want) list[off + __popc(m & ((1u << lane) - 1u))] = (r << kIndexShardShift) | i;
     }
   }
 }

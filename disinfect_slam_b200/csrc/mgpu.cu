@@ -278,22 +278,25 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
     {
       const char* ex = getenv("TSDF_MGPU_EXCHANGE");
       m->fused = m->replicas || !(ex && !strcmp(ex, "nccl"));
-      // How the march gets at foreign TSDF samples.  Default: pulled cache (before the march every rank fetches the TSDF
-      // planes of the foreign blocks its rays can meet: about a room's worth, a few MB).  TSDF_MGPU_MIRROR=push: mirrors
-      // written by the owners' integrate kernels (every rank receives every update of every frame: NVLink-ingress bound
-      // beyond 2 GPUs); =0: neither, every foreign sample is a load over NVLink.  The NCCL-exchange variant keeps the
-      // plain form.
+      // How the march gets at foreign TSDF samples.  Default (push): every rank holds a mirror of every shard's TSDF
+      // planes, kept current by the owners' integrate kernels with posted NVLink stores -- the fastest form measured at
+      // 2 and at 8 GPUs.  TSDF_MGPU_MIRROR=pull: no mirrors; before the march every rank fetches the TSDF planes of the
+      // foreign blocks the view can meet (about a room's worth, a few MB) into a local cache -- less NVLink traffic and
+      // no work in the integrate kernel, but two more kernels per view; =0: neither, every foreign sample is a load over
+      // NVLink (memory per rank = its shard only).  The NCCL-exchange variant keeps the plain form.
       const char* mi = getenv("TSDF_MGPU_MIRROR");
-      m->mirror_mode = world < 2 || m->replicas ? 0 : (mi && !strcmp(mi, "0")) ? 0 : (mi && !strcmp(mi, "push")) ? 1 : (mi && !strcmp(mi, "pull")) ? 2 : (m->fused ? 2 : 0);
+      m->mirror_mode = world < 2 || m->replicas ? 0 : (mi && !strcmp(mi, "0")) ? 0 : (mi && !strcmp(mi, "pull")) ? 2 : (mi && !strcmp(mi, "push")) ? 1 : (m->fused ? 1 : 0);
       const bool want_mirror = m->mirror_mode == 1;
       // Which rows a rank renders: 8-row tiles dealt round-robin (default: every rank gets the same mix of cheap and
       // expensive rows) or TSDF_MGPU_TILES=band, one contiguous band per rank (fewer foreign blocks to fetch, but the
       // ranks finish at different times)
       const char* ti = getenv("TSDF_MGPU_TILES");
       m->row_bands = ti && !strcmp(ti, "band");
-      // Candidate exchange (allocation pass sharded by image tiles): needs the peer barrier, i.e. the fused plane
+      // TSDF_MGPU_ALLOC=exchange: allocation pass sharded by image tiles, candidate keys mailed to their owners (needs the
+      // peer barrier, i.e. the fused plane).  Default (owner): every rank walks all pixel rays and keeps its own blocks --
+      // measured, the barrier the exchange needs costs more than the 20 us of ray walking it saves at 8 GPUs.
       const char* al = getenv("TSDF_MGPU_ALLOC");
-      const bool want_exchange = world > 1 && m->fused && !m->replicas && !(al && !strcmp(al, "owner"));
+      const bool want_exchange = world > 1 && m->fused && !m->replicas && al && !strcmp(al, "exchange");
       std::vector<XBlob> xb(world);
       XBlob mine{};
       CU(cudaIpcGetMemHandle(&mine.h, m->xbuf));

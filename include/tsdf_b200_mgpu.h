@@ -17,19 +17,28 @@
  * NCCL program.  Per frame, on every rank, everything is enqueued on CUDA streams and nothing waits on the host:
  *
  *   integrate   the four planes (15 B/px) are broadcast from the root over NVLink (one grouped ncclBroadcast on a
- *               communication stream, double-buffered so that the broadcast of frame k+1 overlaps the kernels of
- *               frame k), then every rank enumerates the frame but allocates and integrates only the blocks it owns.
- *   raycast     a 4-byte ncclAllReduce on the engine stream is the device-side barrier after every shard's
- *               Integrate; each rank then marches 1/N of the image rows over the WHOLE volume -- blocks of other
- *               shards are read from their owner's HBM over NVLink inside the march kernel (tsdf_raycast_shared),
- *               so the image is bit-identical to a single-GPU render -- and one grouped in-place ncclAllGather
- *               assembles the three images on every rank (it is also the barrier before the next Integrate).
+ *               communication stream, three staging sets, so that the broadcast of frame k+1 overlaps the kernels of
+ *               frame k).  Every rank stages the whole frame but walks the pixel rays of every N-th 32 x 8 tile only
+ *               and mails the candidate block keys to their owners' inboxes (NVLink stores); a peer barrier -- a
+ *               32-thread kernel exchanging flag words with release / acquire at system scope, no collective library
+ *               on the engine stream -- publishes the counts; every owner inserts what it received and integrates the
+ *               blocks it owns (tsdf_alloc_exchange_attach; TSDF_MGPU_ALLOC=owner: every rank walks all rays and
+ *               keeps its own blocks, no barrier).
+ *   raycast     peer barrier (every shard's Integrate has finished); the skip map is built from every shard's pool
+ *               directory; the TSDF planes of the foreign blocks the view can meet are fetched into a local cache with
+ *               bulk NVLink reads (tsdf_shared_cache_attach; TSDF_MGPU_MIRROR=push: mirrors written by the owners'
+ *               integrate kernels instead; =0: every foreign sample is a load over NVLink); each rank marches 1/N of
+ *               the view's 8-row tiles, dealt round-robin (TSDF_MGPU_TILES=band: one contiguous band), over the WHOLE
+ *               volume -- bit-identical to a single-GPU render -- and stores every finished ray into the images of
+ *               ALL ranks (posted NVLink stores); peer barrier.  TSDF_MGPU_EXCHANGE=nccl selects the conventional form
+ *               for comparison: 4-byte ncclAllReduce, local image, grouped in-place ncclAllGather.
  *
- *   TSDF mirrors (default; TSDF_MGPU_MIRROR=0 turns them off): every rank also holds a copy of every shard's TSDF planes
- *               (2 KB per block), which the owners' integrate kernels keep current with posted NVLink stores
- *               (tsdf_mirror_attach).  The march then reads every TSDF sample locally; only the colour and probability of
- *               a hit voxel are fetched from the owner.  Without mirrors a rank's memory holds just its shard (capacity
- *               scales with the GPUs) and the march loads foreign voxels over NVLink sample by sample.
+ *   TSDF_MGPU_MODE=replicas: not sharded at all.  Every rank keeps the WHOLE volume (pool_blocks of cfg must hold it) and
+ *               integrates every frame after the same broadcast; view k is rendered by rank k % world with the plain
+ *               single-GPU kernels, straight into rank 0's image memory.  No barrier inside a tsdf_mgpu_run_sequence;
+ *               a stand-alone tsdf_mgpu_raycast ends with one.  Images, gathers and counters are those of rank 0
+ *               (every replica's are identical).  It multiplies view throughput for volumes that fit one GPU; it adds
+ *               no capacity.  tsdf_mgpu_raycast_composite is not available in this mode.
  *
  * Status codes are those of tsdf_b200.h; tsdf_mgpu_last_error() describes the last failure of the calling thread.
  */
@@ -101,7 +110,9 @@ int tsdf_mgpu_counters(tsdf_mgpu_handle h, tsdf_counters* last_frame_sum, tsdf_c
  * frames.  For i in [first, first + count): frame = frames[i % n_frames]; tsdf_mgpu_integrate(frame), then
  * raycast_mode 1: tsdf_mgpu_raycast from the frame's camera, 2: tsdf_mgpu_raycast_composite, 0: no view.
  * Every rank passes the same cameras; plane pointers are read on `root` only.  Returns after enqueueing (the host only
- * ever waits for the frame two steps back, which bounds the pipeline depth). */
+ * ever waits for the frame two steps back, which bounds the pipeline depth).  Inside a sequence the barrier that ends a
+ * view is supplied by the next frame's candidate-exchange barrier (nothing before it touches the volume or the images),
+ * so a frame with a view costs two barriers, not three; the last view of the sequence ends with its own. */
 typedef struct tsdf_mgpu_frame {
   const void *rgb, *depth, *ht, *lt; /* root only; host or device memory according to planes_on_device */
   float q_xyzw[4];
@@ -116,8 +127,9 @@ int tsdf_mgpu_synchronize(tsdf_mgpu_handle h);
 
 /* Collective timing.  While enabled every NCCL call is bracketed by CUDA events on its stream; the getter (which
  * synchronises) returns device milliseconds and call counts summed since enabling:
- *   [0] frame broadcast  [1] pre-raycast barrier (4-byte all-reduce)  [2] image all-gather  [3] composite all-reduce
- *   [4] shared-volume raycast kernels (skip map over all shards + march)  [5] gather send / recv */
+ *   [0] frame broadcast  [1] barrier before the march (peer barrier kernel / 4-byte all-reduce)  [2] barrier after the
+ *   march / image all-gather  [3] composite all-reduce  [4] shared-volume raycast kernels (skip map over all shards,
+ *   TSDF fetch, march + scatter)  [5] gather send / recv  [6] candidate-exchange barrier of a frame */
 int tsdf_mgpu_set_profiling(tsdf_mgpu_handle h, int enabled);
 int tsdf_mgpu_get_comm_ms(tsdf_mgpu_handle h, float out_ms[8], int64_t out_count[8]);
 

@@ -153,11 +153,14 @@ def test_data_plane_with_one_shard_matches_oracle(tsdf_lib):
 
 
 VARIANTS = {
-    # the product path: peer-barrier kernels, allocation pass sharded by image tiles with the candidate keys mailed to
-    # their owners, one band of rows per rank marched over a pulled TSDF cache, rows stored into every rank's images
+    # the default: peer-barrier kernels, owner-filtered allocation on every rank, TSDF mirrors pushed by the integrate
+    # kernels, 8-row tiles dealt round-robin, rows stored into every rank's images by the march kernel
     "fused": {},
-    # round-robin tiles over TSDF mirrors pushed by the integrate kernels, owner-filtered allocation on every rank
-    "fused-push-mirrors": {"TSDF_MGPU_MIRROR": "push", "TSDF_MGPU_ALLOC": "owner"},
+    # allocation pass sharded by image tiles with the candidate keys mailed to their owners; foreign TSDF planes fetched
+    # into a local cache before the march instead of mirrors
+    "fused-pull-cache-exchange": {"TSDF_MGPU_MIRROR": "pull", "TSDF_MGPU_ALLOC": "exchange"},
+    # the same with one contiguous band of rows per rank
+    "fused-pull-cache-bands": {"TSDF_MGPU_MIRROR": "pull", "TSDF_MGPU_ALLOC": "exchange", "TSDF_MGPU_TILES": "band"},
     # no local TSDF copy at all: every foreign sample is a load over NVLink
     "fused-remote-loads": {"TSDF_MGPU_MIRROR": "0"},
     # ncclAllReduce barrier + in-place ncclAllGather (kept for comparison)
@@ -206,7 +209,7 @@ def test_two_processes_nccl_and_cuda_ipc_match_oracle(tsdf_lib, variant):
         check_replicas_against_oracle(res, world, synth.config(CFG), N_FRAMES)
     else:
         check_against_oracle(res, world, synth.config(CFG), N_FRAMES,
-                             exchange_barriers=N_FRAMES if variant in ("fused", "fused-remote-loads") else 0)
+                             exchange_barriers=N_FRAMES if "exchange" in variant or "bands" in variant else 0)
 
 
 def test_two_threads_of_a_pure_cpp_process_match_oracle(tsdf_lib, tmp_path):
