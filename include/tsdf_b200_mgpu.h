@@ -18,20 +18,23 @@
  *
  *   integrate   the four planes (15 B/px) are broadcast from the root over NVLink (one grouped ncclBroadcast on a
  *               communication stream, three staging sets, so that the broadcast of frame k+1 overlaps the kernels of
- *               frame k).  Every rank stages the whole frame but walks the pixel rays of every N-th 32 x 8 tile only
- *               and mails the candidate block keys to their owners' inboxes (NVLink stores); a peer barrier -- a
- *               32-thread kernel exchanging flag words with release / acquire at system scope, no collective library
- *               on the engine stream -- publishes the counts; every owner inserts what it received and integrates the
- *               blocks it owns (tsdf_alloc_exchange_attach; TSDF_MGPU_ALLOC=owner: every rank walks all rays and
- *               keeps its own blocks, no barrier).
- *   raycast     peer barrier (every shard's Integrate has finished); the skip map is built from every shard's pool
- *               directory; the TSDF planes of the foreign blocks the view can meet are fetched into a local cache with
- *               bulk NVLink reads (tsdf_shared_cache_attach; TSDF_MGPU_MIRROR=push: mirrors written by the owners'
- *               integrate kernels instead; =0: every foreign sample is a load over NVLink); each rank marches 1/N of
- *               the view's 8-row tiles, dealt round-robin (TSDF_MGPU_TILES=band: one contiguous band), over the WHOLE
- *               volume -- bit-identical to a single-GPU render -- and stores every finished ray into the images of
- *               ALL ranks (posted NVLink stores); peer barrier.  TSDF_MGPU_EXCHANGE=nccl selects the conventional form
- *               for comparison: 4-byte ncclAllReduce, local image, grouped in-place ncclAllGather.
+ *               frame k); then every rank enumerates the frame but allocates and integrates only the blocks it owns,
+ *               and its integrate kernel also stores every TSDF value it updates into the TSDF mirrors of all ranks
+ *               (posted NVLink stores, tsdf_mirror_attach).
+ *               TSDF_MGPU_ALLOC=exchange: every rank stages the whole frame but walks the pixel rays of every N-th
+ *               32 x 8 tile only and mails the candidate block keys to their owners' inboxes; a peer barrier publishes
+ *               the counts; the owners insert (tsdf_alloc_exchange_attach).
+ *   raycast     peer barrier -- a 32-thread kernel exchanging flag words with release / acquire at system scope, no
+ *               collective library on the engine stream -- (every shard's Integrate has finished); the skip map is built
+ *               from every shard's pool directory; each rank marches 1/N of the view's 8-row tiles, dealt round-robin
+ *               (TSDF_MGPU_TILES=band: one contiguous band), over the WHOLE volume: TSDF samples from the local mirror,
+ *               the colour and probability of a hit voxel from its owner over NVLink -- bit-identical to a single-GPU
+ *               render -- and stores every finished ray into the images of ALL ranks (posted NVLink stores); peer barrier.
+ *               TSDF_MGPU_MIRROR=pull: no mirrors; before the march the TSDF planes of the foreign blocks the view can
+ *               meet are fetched into a local cache with bulk NVLink reads (tsdf_shared_cache_attach); =0: every foreign
+ *               sample is a load over NVLink, a rank's memory holds just its shard.
+ *               TSDF_MGPU_EXCHANGE=nccl selects the conventional form for comparison: 4-byte ncclAllReduce, local
+ *               image, grouped in-place ncclAllGather.
  *
  *   TSDF_MGPU_MODE=replicas: not sharded at all.  Every rank keeps the WHOLE volume (pool_blocks of cfg must hold it) and
  *               integrates every frame after the same broadcast; view k is rendered by rank k % world with the plain
@@ -110,9 +113,9 @@ int tsdf_mgpu_counters(tsdf_mgpu_handle h, tsdf_counters* last_frame_sum, tsdf_c
  * frames.  For i in [first, first + count): frame = frames[i % n_frames]; tsdf_mgpu_integrate(frame), then
  * raycast_mode 1: tsdf_mgpu_raycast from the frame's camera, 2: tsdf_mgpu_raycast_composite, 0: no view.
  * Every rank passes the same cameras; plane pointers are read on `root` only.  Returns after enqueueing (the host only
- * ever waits for the frame two steps back, which bounds the pipeline depth).  Inside a sequence the barrier that ends a
- * view is supplied by the next frame's candidate-exchange barrier (nothing before it touches the volume or the images),
- * so a frame with a view costs two barriers, not three; the last view of the sequence ends with its own. */
+ * ever waits for the frame two steps back, which bounds the pipeline depth).  With TSDF_MGPU_ALLOC=exchange the barrier
+ * that ends a view is supplied, inside a sequence, by the next frame's candidate-exchange barrier (nothing before it
+ * touches the volume or the images): a frame with a view costs two barriers, not three. */
 typedef struct tsdf_mgpu_frame {
   const void *rgb, *depth, *ht, *lt; /* root only; host or device memory according to planes_on_device */
   float q_xyzw[4];
