@@ -92,3 +92,54 @@ def test_raycast_and_gather_match_reference_kernels(tsdf_lib):
     assert len(a) > 0 and a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     g.close()
     r.close()
+
+
+def test_reference_as_shipped_agrees_within_tolerance(tsdf_lib):
+    """The bit-exact pin above is the reference compiled WITHOUT FMA contraction.  The reference as its own build
+    compiles it (nvcc's default contraction, oracle/_ref/libref_tsdf.so -- the timing baseline of `bench.py --impl
+    reference`) rounds a few projections differently, so a voxel now and then takes the neighbouring pixel or a block
+    at the edge of the truncation band appears one frame earlier or later.  That cannot be bit-identical; this test
+    bounds how far apart the two volumes are after six frames, the reference's lock losers included (blocks
+    it allocates a frame late, 2.4 % here, carry one update less): no reference-only block, and on the common blocks
+    nearly all voxels equal to 1e-5 of the truncation-normalised TSDF with equal weights.  Measured on B200:
+    0.76 % of the observed voxels differ by more than 1e-5, 0.34 % by more than 1e-2, weights differ on 0.74 %."""
+    from disinfect_slam_b200 import tsdf_grid
+    from oracle import ref_cuda as rc_mod
+    if not rc_mod.available(False):
+        pytest.fail("oracle/_ref/libref_tsdf.so is missing: run __graft_entry__.build() where /root/reference exists")
+    cfg = synth.config("tiny")
+    sc = synth.Scene(cfg)
+    g = tsdf_grid.TSDFGrid(cfg.voxel_size, cfg.truncation, pool_blocks=cfg.pool_blocks, table_slots=cfg.table_slots)
+    r = rc_mod.RefTSDFGrid(cfg.voxel_size, cfg.truncation, parity=False)
+    for i in range(6):
+        f = sc.frame(i)
+        r.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"])
+        g.Integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], (f["q"], f["t"]))
+    ek, et, ec, ep = g.export()
+    rk, rt, rcol, rp = r.export()
+    es, rs = keyset(ek), keyset(rk)
+    common = sorted(es & rs)
+    ei = {k: j for j, k in enumerate(map(tuple, ek.tolist()))}
+    ri = {k: j for j, k in enumerate(map(tuple, rk.tolist()))}
+    a = np.array([ei[k] for k in common]); b = np.array([ri[k] for k in common])
+    seen = (ec[a][..., 3] > 0) & (rcol[b][..., 3] > 0)
+    dt = np.abs(et[a].astype(np.float64) - rt[b])[seen]
+    stats = {
+        "blocks_engine": len(es), "blocks_reference": len(rs),
+        "reference_only_frac": len(rs - es) / max(len(rs), 1), "engine_only_frac": len(es - rs) / max(len(es), 1),
+        "tsdf_frac_above_1e-5": float((dt > 1e-5).mean()), "tsdf_frac_above_1e-2": float((dt > 1e-2).mean()), "tsdf_max": float(dt.max(initial=0)),
+        "weight_differs_frac": float((ec[a][..., 3] != rcol[b][..., 3]).mean()),
+        "colour_differs_by_more_than_1_frac": float((np.abs(ec[a][..., :3].astype(int) - rcol[b][..., :3].astype(int)).max(-1)[seen] > 1).mean()),
+        "prob_max": float(np.abs(ep[a].astype(np.float64) - rp[b])[seen].max(initial=0)),
+    }
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "reference_default_flags_stats.json"), "w") as fh:
+            json.dump(stats, fh)
+    g.close()
+    r.close()
+    assert stats["reference_only_frac"] <= 0.02 and stats["engine_only_frac"] <= 0.10, stats  # (engine-only includes the reference's lock losers)
+    assert stats["tsdf_frac_above_1e-5"] <= 0.03 and stats["tsdf_frac_above_1e-2"] <= 0.015, stats
+    assert stats["weight_differs_frac"] <= 0.03 and stats["colour_differs_by_more_than_1_frac"] <= 0.03, stats
