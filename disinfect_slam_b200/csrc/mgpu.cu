@@ -281,8 +281,8 @@ int tsdf_mgpu_create(float voxel_size, float truncation, const tsdf_config* user
       // How the march gets at foreign TSDF samples.  Default (push): every rank holds a mirror of every shard's TSDF
       // planes, kept current by the owners' integrate kernels with posted NVLink stores -- the fastest form measured at
       // 2 and at 8 GPUs.  TSDF_MGPU_MIRROR=pull: no mirrors; before the march every rank fetches the TSDF planes of the
-      // foreign blocks the view can meet (about a room's worth, a few MB) into a local cache -- less NVLink traffic and
-      // no work in the integrate kernel, but two more kernels per view; =0: neither, every foreign sample is a load over
+      // foreign blocks the view can meet (about a room's worth, a few MB) into a local cache -- no remote stores in the
+      // integrate kernel, but two more kernels per view and a stamp check per sample; =0: neither, every foreign sample is a load over
       // NVLink (memory per rank = its shard only).  The NCCL-exchange variant keeps the plain form.
       const char* mi = getenv("TSDF_MGPU_MIRROR");
       m->mirror_mode = world < 2 || m->replicas ? 0 : (mi && !strcmp(mi, "0")) ? 0 : (mi && !strcmp(mi, "pull")) ? 2 : (mi && !strcmp(mi, "push")) ? 1 : (m->fused ? 1 : 0);

@@ -228,8 +228,11 @@ int tsdf_mirror_attach(tsdf_handle h, int world, void* const* mirrors, int strid
  * against every shard's pool directory -- with bulk NVLink reads, and stamp them; the march then samples them locally.
  * A sample of a foreign block without a current stamp is read from its owner, so results do not depend on the test.
  * Entries stay valid across views while the caller passes peers_unchanged = 1.  What a view can meet is bounded by
- * max_depth, about a room's worth of blocks (a few MB per view and rank), whereas mirrors make every rank receive every
- * update of every frame; a contiguous band of rows (tile_stride 1) needs about 1/shard_count of that.  pad_voxels = how far the test grows every block (3 covers the nearest-voxel rounding, the
+ * max_depth, about a room's worth of blocks (a few MB per view and rank); a contiguous band of rows (tile_stride 1)
+ * needs about 1/shard_count of that.  Mirrors move about as little (only updated voxels travel) and measured faster
+ * (DESIGN.md section 7); the cache keeps the integrate kernel free of remote stores and is the starting point for a
+ * bounded-size cache (today it is addressed like a mirror and as large).
+ * pad_voxels = how far the test grows every block (3 covers the nearest-voxel rounding, the
  * gradient samples and the float accumulation; smaller or negative values are still exact, only slower).
  * stride_blocks == 0 detaches and frees. */
 int tsdf_shared_cache_attach(tsdf_handle h, int stride_blocks, int pad_voxels);
