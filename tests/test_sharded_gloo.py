@@ -169,3 +169,71 @@ def test_two_rank_sharding_matches_single_volume(tsdf_lib):
     nfrac = (res[0]["normal"][exact] != normal[exact]).any(-1).mean()
     print(f"sharded raycast: of the identical hits {cfrac:.4f} differ in colour, {nfrac:.4f} in the shaded normal")
     assert cfrac < 0.02 and nfrac < 0.15
+
+
+# ---- candidate exchange (TSDF_MGPU_ALLOC=exchange, csrc/kernels_integrate.cu: frame_allocate_kernel<true> +
+# insert_candidates_kernel): the protocol, restated with the oracle and carried by gloo ----------------------------
+def _exchange_worker(rank, world, port, q):
+    """Rank r walks the pixel rays of the 32 x 8 tiles dealt to it (tile index mod world), mails every candidate block to
+    its owner, and the owner inserts the ones it does not hold.  Checked frame by frame against the single volume: what
+    an owner ends up inserting must be exactly the single volume's new blocks that it owns."""
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    cfg = synth.config(CFG)
+    sc = synth.Scene(cfg)
+    single = Oracle(cfg.voxel_size, cfg.truncation)   # the unsharded truth, kept by every rank
+    shard = OracleShard(cfg, rank, world, SHIFT)      # this rank's blocks
+    ty, tx = np.mgrid[0:cfg.height, 0:cfg.width]
+    tiles_x = (cfg.width + 31) // 32
+    mine = ((ty // 8) * tiles_x + tx // 32) % world == rank
+    ok, n_mailed, n_inserted = True, 0, 0
+    for i in range(N_FRAMES + 2):
+        f = sc.frame(i)
+        # (1) candidates of this rank's tiles: a scratch volume that is empty, so every candidate is absent, fed the
+        #     frame with the other ranks' pixels invalidated (depth 0 = no ray, voxel_tsdf.cu:121)
+        scratch = Oracle(cfg.voxel_size, cfg.truncation)
+        cand = scratch.integrate(f["rgb"], np.where(mine, f["depth"], 0).astype(np.float32), f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"],
+                                 want_new_keys=True)["new_keys"]
+        scratch.close()
+        owner = tsdf_grid.block_owner(cand, world, SHIFT) if len(cand) else np.zeros(0, np.int64)
+        # (2) the mail run: keys to their owners (gloo stands in for the NVLink stores + peer barrier)
+        outbox = [cand[owner == r] for r in range(world)]
+        boxes = [None] * world
+        dist.all_gather_object(boxes, outbox)
+        inbox = np.concatenate([b[rank] for b in boxes]) if boxes else np.zeros((0, 3), np.int16)
+        n_mailed += int(sum(len(o) for o in outbox))
+        # (3) the owner inserts what it does not hold yet
+        have = set(map(tuple, shard.o.export(voxels=False)[0].tolist()))
+        inserted = {tuple(k) for k in inbox.tolist()} - have
+        # the single volume's verdict for this frame
+        truth_new = single.integrate(f["rgb"], f["depth"], f["ht"], f["lt"], cfg.max_depth, f["K"], f["q"], f["t"], want_new_keys=True)["new_keys"]
+        truth_mine = {tuple(k) for k in truth_new[tsdf_grid.block_owner(truth_new, world, SHIFT) == rank].tolist()} if len(truth_new) else set()
+        ok = ok and inserted == truth_mine
+        n_inserted += len(inserted)
+        for k in inserted:
+            shard.o.allocate_block(*k)
+        # (4) the frame itself (OracleShard re-derives the same block set and drops what it does not own)
+        shard.integrate({k: torch.from_numpy(np.ascontiguousarray(f[k]).reshape(-1)) for k in ("rgb", "depth", "ht", "lt")},
+                        cfg.width, cfg.height, cfg.max_depth, f["K"], f["q"], f["t"])
+        owned_truth = single.export(voxels=False)[0]
+        owned_truth = owned_truth[tsdf_grid.block_owner(owned_truth, world, SHIFT) == rank]
+        ok = ok and np.array_equal(shard.o.export(voxels=False)[0], owned_truth)
+    q.put((rank, dict(ok=ok, mailed=n_mailed, inserted=n_inserted)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_candidate_exchange_protocol_matches_single_volume(tsdf_lib):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert res[r]["ok"], f"rank {r}: the blocks inserted from the inbox differ from the single volume's new blocks it owns"
+        assert res[r]["mailed"] > 0 and res[r]["inserted"] > 0
